@@ -1,0 +1,133 @@
+/*
+ * vavae_b200.h -- C ABI of the B200-native LightningDiT sampling engine.
+ *
+ * The reference (heimaoqqq/VA-VAE) is pure Python/PyTorch and has no FFI of its own for this
+ * path; these entry points are what a ctypes binding behind the reference's Python objects
+ * binds (INTEGRATION.md shows the stub).  Each function names the reference interface it
+ * replaces (paths relative to /root/reference/LightningDiT/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  All tensors are dense, row-major.
+ *   - "device" pointers are CUDA device pointers valid on the engine's GPU for the duration of
+ *     the call (borrowed; the caller -- e.g. PyTorch -- owns them).  Outputs are pre-allocated
+ *     by the caller.  The engine owns packed weights and workspace.
+ *   - every call enqueues on the caller-supplied CUDA stream (pass the raw cudaStream_t as
+ *     void*, 0 = legacy default stream) and does not synchronise, except the *_host calls,
+ *     which return host data and therefore synchronise the stream before returning.
+ *   - return value: 0 on success, non-zero on error; vavae_last_error() gives the message of
+ *     the last failure on the calling thread.  One engine per (process, GPU); not re-entrant.
+ */
+#ifndef VAVAE_B200_H
+#define VAVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAVAE_ABI_VERSION 1
+
+/* precision modes */
+#define VAVAE_PREC_BF16 0 /* tcgen05 bf16 tensor-core path, fp32 accumulate / residual / statistics */
+#define VAVAE_PREC_FP32 1 /* fp32 SIMT validation path (parity <= 1e-5 vs the fp32 reference)       */
+
+/* ODE methods (fixed grid), transport/integrators.py:118-125 -> torchdiffeq.odeint(method=...) */
+#define VAVAE_ODE_EULER 0
+#define VAVAE_ODE_HEUN 1
+
+typedef struct vavae_engine vavae_engine_t;
+
+/* Constructor arguments of LightningDiT, models/lightningdit.py:279-297 (same names, same meaning). */
+typedef struct vavae_config {
+  int32_t abi_version; /* must be VAVAE_ABI_VERSION */
+  int32_t input_size;
+  int32_t patch_size;
+  int32_t in_channels;
+  int32_t hidden_size;
+  int32_t depth;
+  int32_t num_heads;
+  int32_t mlp_hidden;  /* int(2/3*int(D*mlp_ratio)) if use_swiglu else int(D*mlp_ratio); lightningdit.py:213-224 */
+  int32_t num_classes;
+  int32_t label_rows;  /* rows of y_embedder.embedding_table: num_classes + (class_dropout_prob > 0) */
+  int32_t learn_sigma;
+  int32_t use_qknorm;
+  int32_t use_swiglu;
+  int32_t use_rope;
+  int32_t use_rmsnorm;
+  int32_t wo_shift;
+  int32_t precision;      /* VAVAE_PREC_* */
+  int32_t max_chunk_rows; /* model rows processed per pass of the layer stack (0 = engine default) */
+} vavae_config_t;
+
+/* Replaces LightningDiT.__init__ (models/lightningdit.py:279-338): allocates the engine on CUDA `device`. */
+int vavae_create(const vavae_config_t* cfg, int device, vavae_engine_t** out);
+int vavae_destroy(vavae_engine_t* e);
+
+/* Replaces nn.Module.load_state_dict (inference.py:88-93): copy one fp32 tensor of the reference
+ * state_dict (key names / shapes: SURVEY.md section 8b; nn.Linear (out,in) layout) into the engine.
+ * `data` is a host pointer if is_device == 0, else a device pointer.  The extra key
+ * "t_embedder.freqs" (128 floats, lightningdit.py:121-123) carries the sinusoid frequencies. */
+int vavae_load_weight(vavae_engine_t* e, const char* name, const float* data, const int64_t* shape, int ndim,
+                      int is_device);
+/* Packs weights for the selected precision (bf16 cast, w12 row interleave, K padding, batched
+ * adaLN matrix, TMA descriptors) and allocates workspace.  Must follow the last load_weight. */
+int vavae_finalize(vavae_engine_t* e, void* stream);
+
+/* Replaces LightningDiT.forward(x, t, y), models/lightningdit.py:391-418.
+ * x: (batch, C, H, W) f32 device; t: (batch,) f32 device; y: (batch,) int64 device; out: (batch, C, H, W) f32 device. */
+int vavae_forward(vavae_engine_t* e, const float* x, const float* t, const int64_t* y, float* out, int batch,
+                  void* stream);
+
+/* Replaces LightningDiT.forward_with_cfg, models/lightningdit.py:420-442.  batch = 2n rows; only x[:n] is read.
+ * cfg_interval: 0 = None/False, 1 = True (guidance only when t[0] >= cfg_interval_start).
+ * cfg_channels: number of leading channels that receive guidance (reference: 3, lightningdit.py:432). */
+int vavae_forward_with_cfg(vavae_engine_t* e, const float* x, const float* t, const int64_t* y, float cfg_scale,
+                           int cfg_interval, float cfg_interval_start, int cfg_channels, float* out, int batch,
+                           void* stream);
+
+/* Replaces sample_fn = Sampler.sample_ode(...) -> ode.sample (transport/transport.py:398-443,
+ * transport/integrators.py:107-126) driving model.forward_with_cfg (use_cfg=1) or model.forward (use_cfg=0)
+ * over the fixed grid `t_grid` (HOST pointer, n_points fp32 values as built by integrators.py:94-101).
+ * z, out_final: (batch, C, H, W) f32 device; y: (batch,) int64 device.  With use_cfg=1 batch = 2n as in
+ * inference.py:205-211.  out_final receives the last grid point ([-1] of the reference trajectory).
+ * out_trace: optional (NULL to skip) device buffer of (n_evals, batch, C, H, W) f32 receiving every
+ * evaluation's velocity in call order (n_evals = n_points-1 for Euler, 2*(n_points-1) for Heun). */
+int vavae_sample_ode(vavae_engine_t* e, const float* z, const int64_t* y, const float* t_grid, int n_points,
+                     int method, int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start,
+                     int cfg_channels, float* out_final, float* out_trace, int batch, void* stream);
+
+/* Same as vavae_sample_ode with HOST buffers for z, y and out_final (H2D / D2H copies inside the call;
+ * synchronises the stream before returning).  This is the end-to-end entry bench.py times as `e2e`. */
+int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t* y_host, const float* t_grid,
+                          int n_points, int method, int use_cfg, float cfg_scale, int cfg_interval,
+                          float cfg_interval_start, int cfg_channels, float* out_final_host, int batch, void* stream);
+
+/* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
+uint64_t vavae_launch_count(const vavae_engine_t* e);
+/* Bytes of device memory the engine owns (weights + workspace). */
+uint64_t vavae_device_bytes(const vavae_engine_t* e);
+const char* vavae_last_error(void);
+int vavae_abi_version(void);
+
+/* ---- kernel-level test / measurement entry points (tests/ and bench.py; not needed by a drop-in) ---- */
+
+/* C[M,N] (f32) = A[M,K] (bf16) * W[N,K]^T (bf16) + bias[N] (f32, may be NULL) on the tcgen05 GEMM. */
+int vavae_test_gemm_bf16(const void* A, const void* W, const float* bias, float* C, int M, int N, int K,
+                         void* stream);
+/* O[B*T, H*hd] (bf16) = softmax(q k^T / sqrt(hd)) v on the tcgen05 attention kernel.
+ * q, k: (B,H,T,hd_pad) bf16; vt: (B,H,hd_v_pad,T) bf16 (see DESIGN.md "attention layouts"). */
+int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int T, int hd,
+                              void* stream);
+/* Selects where the attention kernel keeps the bf16 probabilities P: 1 = tensor memory (TS MMA, default),
+ * 0 = 128B-swizzled shared memory (SS MMA).  Process-wide. */
+int vavae_set_attention_variant(int p_in_tmem);
+/* Per-kernel timing: runs the named kernel of the engine's own layer 0 `iters` times on the given
+ * number of model rows with CUDA events on `stream`; returns mean milliseconds per launch in *ms. */
+int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAVAE_B200_H */

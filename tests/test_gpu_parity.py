@@ -1,0 +1,197 @@
+"""Engine parity on the B200, through the C ABI (ctypes -> libvavae_b200.so):
+  * against fixtures produced by the UNMODIFIED reference (tests/golden, oracle/gen_golden.py);
+  * against the CPU oracle on seeded inputs at BASELINE.json's model sizes.
+Tolerances are BASELINE.json's: per-evaluation velocity rel-L2 <= 1e-5 (fp32 validation mode) and
+<= 1e-2 (bf16 tensor-core mode) versus the fp32 reference."""
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, rel_l2
+from oracle import lightningdit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 1e-2}
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (run with -m gpu on the B200 box)")
+    return torch.device("cuda", 0)
+
+
+def _model_from_fixture(fix, precision, **kw):
+    import va_vae_b200 as V
+    m = V.LightningDiT(**fix["ctor"], precision=precision, **kw)
+    missing = m.load_state_dict(fix["state_dict"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.eval().to(_dev())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_forward_matches_reference_fixture(golden, name, precision):
+    fix = golden(name)
+    m = _model_from_fixture(fix, precision)
+    out = m(fix["x"].cuda(), fix["t"].cuda(), fix["y"].cuda())
+    err = rel_l2(out, fix["forward"])
+    assert out.shape == fix["forward"].shape
+    assert err < TOL[precision], f"{name}/{precision}: forward rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_forward_with_cfg_matches_reference_fixture(golden, name, precision):
+    fix = golden(name)
+    m = _model_from_fixture(fix, precision)
+    x, y = fix["x"].cuda(), fix["y"].cuda()
+    n2 = x.shape[0]
+    for key, t, kw in (("cfg_guided", fix["t_uniform"], dict(cfg_interval=True, cfg_interval_start=0.11)),
+                       ("cfg_gated_off", torch.full((n2,), 0.05), dict(cfg_interval=True, cfg_interval_start=0.11)),
+                       ("cfg_no_interval", torch.full((n2,), 0.05), {})):
+        out = m.forward_with_cfg(x, t.cuda(), y, 4.0, **kw)
+        err = rel_l2(out, fix[key])
+        assert err < TOL[precision] * (4 if precision == "bf16" else 1), f"{name}/{precision}/{key}: rel-L2 {err:.3e}"
+        n = n2 // 2
+        assert torch.equal(out[:n, :3], out[n:, :3])      # guided channels duplicated (lightningdit.py:441)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("method,steps,shift", [("euler", 6, 0.3), ("heun", 4, 0.1), ("euler", 5, 0.0)])
+def test_sampler_matches_reference_fixture(golden, name, precision, method, steps, shift):
+    import va_vae_b200 as V
+    fix = golden(name)
+    m = _model_from_fixture(fix, precision)
+    n = fix["x"].shape[0] // 2
+    z = torch.cat([fix["x"][:n], fix["x"][:n]], 0).cuda()
+    sampler = V.Sampler(V.create_transport("Linear", "velocity", None, None, None))
+    fn = sampler.sample_ode(sampling_method=method, num_steps=steps, atol=1e-6, rtol=1e-3, reverse=False,
+                            timestep_shift=shift)
+    assert torch.equal(fn.__self__.t, fix[f"grid_{method}_{steps}_{shift}"])
+    out = fn(z, m.forward_with_cfg, y=fix["y"].cuda(), cfg_scale=4.0, cfg_interval=True, cfg_interval_start=0.11)[-1]
+    err = rel_l2(out, fix[f"sample_{method}_{steps}_{shift}"])
+    assert err < TOL[precision], f"{name}/{precision}/{method}: final-latent rel-L2 {err:.3e}"
+    samples, _ = out.chunk(2, dim=0)                      # inference.py:217-218 keeps working
+    assert samples.shape[0] == n
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sampler_nocfg_and_generic_loop(golden, precision):
+    import va_vae_b200 as V
+    fix = golden("tiny_prod")
+    m = _model_from_fixture(fix, precision)
+    sampler = V.Sampler(V.create_transport("Linear", "velocity", None, None, None))
+    fn = sampler.sample_ode(sampling_method="euler", num_steps=4, atol=1e-6, rtol=1e-3, reverse=False, timestep_shift=0.3)
+    x, y = fix["x"].cuda(), fix["y"].cuda()
+    native = fn(x, m.forward, y=y)[-1]
+    assert rel_l2(native, fix["sample_nocfg_euler_4_0.3"]) < TOL[precision]
+    # any other callable goes through the generic fixed-grid loop and returns the full trajectory tensor
+    traj = fn(x, lambda xx, tt, **kw: m.forward(xx, tt, **kw), y=y)
+    assert traj.shape == (4,) + tuple(x.shape)
+    assert rel_l2(traj[-1], fix["sample_nocfg_euler_4_0.3"]) < TOL[precision]
+
+
+def _oracle_case(name, n, seed_w=0, **kw):
+    cfg = O.config_from_name(name, input_size=16, **kw)
+    sd = O.init_state_dict(cfg, seed=seed_w)
+    z = torch.randn(n, 32, 16, 16, generator=torch.Generator().manual_seed(1234))
+    y = torch.randint(0, cfg.num_classes, (n,), generator=torch.Generator().manual_seed(4321))
+    return cfg, sd, z, y
+
+
+def _engine_model(name, cfg, sd, precision):
+    import va_vae_b200 as V
+    m = V.LightningDiT_models[name](input_size=16, num_classes=cfg.num_classes, in_channels=32, use_qknorm=cfg.use_qknorm,
+                                    use_swiglu=True, use_rope=True, use_rmsnorm=True, wo_shift=False, precision=precision)
+    m.load_state_dict(sd, strict=True)
+    return m.eval().to(_dev())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config1_S1_full_trajectory_vs_oracle(precision):
+    """BASELINE.json configs[0]: S/1, n=4, 10-point Euler + CFG (interval 0.11, shift 0.1): every evaluation's
+    velocity and the final latent against the CPU oracle."""
+    cfg, sd, z, y = _oracle_case("LightningDiT-S/1", 4, num_classes=31)
+    zz = torch.cat([z, z], 0)
+    yy = torch.cat([y, torch.full((4,), 31)])
+    grid = O.time_grid(10, 0.1)
+    ref_final, ref_trace = O.sample_ode(cfg, sd, zz, yy, grid, "euler", 10.0, True, 0.11, return_trace=True)
+    m = _engine_model("LightningDiT-S/1", cfg, sd, precision)
+    out, trace = m.engine().sample_ode(zz.cuda(), yy.cuda(), grid, "euler", True, 10.0, True, 0.11, 3, return_trace=True)
+    worst = max(rel_l2(trace[i][:4], ref_trace[i][:4]) for i in range(len(ref_trace)))
+    final = rel_l2(out[:4], ref_final[:4])
+    print(f"S/1 {precision}: max per-eval velocity rel-L2 {worst:.3e}, final-latent rel-L2 {final:.3e}")
+    assert len(ref_trace) == 9 and trace.shape[0] == 9
+    assert worst < TOL[precision], f"per-eval velocity rel-L2 {worst:.3e}"
+    assert final < TOL[precision] * 2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name,qknorm", [("LightningDiT-B/1", False), ("LightningDiT-XL/1", False), ("LightningDiT-XL/1", True)])
+def test_single_evals_vs_oracle(name, qknorm, precision):
+    """B/1 and XL/1 (head_dim 72): forward_with_cfg at several t on n=2 against the CPU oracle; short Heun run."""
+    cfg, sd, z, y = _oracle_case(name, 2, num_classes=1000, use_qknorm=qknorm)
+    zz = torch.cat([z, z], 0)
+    yy = torch.cat([y, torch.full((2,), 1000)])
+    m = _engine_model(name, cfg, sd, precision)
+    for tval in (0.0, 0.35, 0.9):
+        t = torch.full((4,), tval)
+        ref = O.forward_with_cfg(cfg, sd, zz, t, yy, 10.0)
+        out = m.forward_with_cfg(zz.cuda(), t.cuda(), yy.cuda(), 10.0)
+        err = rel_l2(out[:2], ref[:2])
+        print(f"{name} qknorm={qknorm} {precision} t={tval}: velocity rel-L2 {err:.3e}")
+        assert err < TOL[precision], f"{name} t={tval}: velocity rel-L2 {err:.3e}"
+    grid = O.time_grid(3, 0.3)
+    ref_final = O.sample_ode(cfg, sd, zz, yy, grid, "heun", 10.0)
+    out = m.engine().sample_ode(zz.cuda(), yy.cuda(), grid, "heun", True, 10.0)
+    assert rel_l2(out[:2], ref_final[:2]) < TOL[precision] * 2
+
+
+def test_full_size_properties_bf16():
+    """Size-independent properties at BASELINE.json's batch scale (B/1, 64 samples -> 128 model rows):
+    chunk invariance (the layer stack is run per chunk), determinism, and CFG linearity in the scale."""
+    cfg, sd, z, y = _oracle_case("LightningDiT-B/1", 64, num_classes=31)
+    import va_vae_b200 as V
+    zz = torch.cat([z, z], 0).cuda()
+    yy = torch.cat([y, torch.full((64,), 31)]).cuda()
+    t = torch.full((128,), 0.4).cuda()
+    outs = []
+    for chunk in (128, 32):
+        m = V.LightningDiT_models["LightningDiT-B/1"](input_size=16, num_classes=31, in_channels=32, use_swiglu=True,
+                                                      use_rope=True, use_rmsnorm=True, precision="bf16",
+                                                      max_chunk_rows=chunk)
+        m.load_state_dict(sd)
+        m = m.eval().to(_dev())
+        a = m.forward_with_cfg(zz, t, yy, 1.0)
+        b = m.forward_with_cfg(zz, t, yy, 1.0)
+        assert torch.equal(a, b), "kernels must be deterministic"
+        c = m.forward_with_cfg(zz, t, yy, 3.0)
+        u = m.forward(zz, t, yy)
+        # vhat(s) = u + s (c - u) on the guided channels: s=1 gives the conditional velocity, s=3 extrapolates
+        cond, unc = u[:64, :3], u[64:, :3]
+        assert rel_l2(a[:64, :3], cond) < 1e-6
+        assert rel_l2(c[:64, :3], unc + 3.0 * (cond - unc)) < 1e-5
+        assert torch.equal(c[:64, 3:], u[:64, 3:]) and torch.equal(c[64:, 3:], u[64:, 3:])
+        outs.append(a)
+    assert torch.equal(outs[0], outs[1]), "results must not depend on the chunking of the batch"
+
+
+def test_edge_cases_and_errors():
+    import va_vae_b200 as V
+    cfg, sd, z, y = _oracle_case("LightningDiT-S/1", 1, num_classes=31)
+    m = _engine_model("LightningDiT-S/1", cfg, sd, "bf16")
+    # batch of one row / odd batch through forward
+    t1 = torch.tensor([0.3]).cuda()
+    o1 = m(z.cuda(), t1, y.cuda())
+    ref = O.forward(cfg, sd, z, torch.tensor([0.3]), y)
+    assert rel_l2(o1, ref) < 1e-2
+    with pytest.raises(ValueError):
+        m.forward_with_cfg(torch.zeros(3, 32, 16, 16).cuda(), torch.zeros(3).cuda(), torch.zeros(3, dtype=torch.long).cuda(), 2.0)
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 32, 8, 8).cuda(), torch.zeros(2).cuda(), torch.zeros(2, dtype=torch.long).cuda())
+    with pytest.raises(NotImplementedError):
+        V.Sampler(V.create_transport()).sample_ode(sampling_method="dopri5", num_steps=4)(z.cuda(), m.forward, y=y.cuda())
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(z.cuda(), t1, y.cuda())

@@ -1,0 +1,4 @@
+"""B200-native LightningDiT sampling engine (drop-in for the reference's model + transport sampler API)."""
+from .lightningdit import LightningDiT, LightningDiT_models  # noqa: F401
+from .transport import create_transport, Sampler, Transport, ModelType, PathType, WeightType  # noqa: F401
+from .engine import Engine, load_library, LIB_PATH  # noqa: F401

@@ -1,0 +1,168 @@
+// Shared declarations for the B200 LightningDiT engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <stdexcept>
+
+typedef __nv_bfloat16 bf16;
+
+namespace vv {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define VV_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      throw vv::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                      std::to_string(__LINE__));                                                   \
+  } while (0)
+
+#define VV_CHECK(cond, msg)                                          \
+  do {                                                               \
+    if (!(cond)) throw vv::Error(std::string("check failed: ") + msg); \
+  } while (0)
+
+// Launch bookkeeping: every kernel launch goes through this so bench.py can report gpu_launches.
+struct LaunchCounter {
+  uint64_t n = 0;
+};
+extern thread_local LaunchCounter* g_counter;
+inline void count_launch() {
+  if (g_counter) g_counter->n++;
+}
+#define VV_LAUNCH_CHECK()        \
+  do {                           \
+    vv::count_launch();          \
+    VV_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// Maps a model row of the current chunk to rows of the caller's tensors.  A chunk has up to two
+// segments of `seg_rows` rows: under CFG segment 0 = conditional rows, segment 1 = unconditional
+// rows of the SAME samples (both read the same latent rows, lightningdit.py:425-426).
+struct RowMap {
+  int seg_rows;
+  int x_off[2];    // row offset into the latent input
+  int y_off[2];    // offset into labels
+  int t_off[2];    // offset into t (multiplied by t_stride)
+  int out_off[2];  // row offset into the velocity output
+  int t_stride;    // 0: every row uses t[0]
+};
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- epilogue selectors for the SIMT fp32 GEMM
+enum F32Epi { F32_EPI_NONE = 0, F32_EPI_SILU = 1, F32_EPI_GELU_TANH = 2, F32_EPI_ADD_LABEL_SILU = 3 };
+
+struct F32GemmArgs {
+  const float* A;  // [M, K]
+  int lda;
+  const float* W;  // [N, K]
+  int ldw;
+  const float* bias;  // [N] or null
+  float* C;           // [M, ldc]
+  int ldc;
+  int M, N, K;
+  int epi;
+  // F32_EPI_ADD_LABEL_SILU: C = bias + acc + table[y[row]] ; also writes silu(C) to C2 (fp32) / C2h (bf16)
+  const float* table;
+  const int64_t* labels;
+  RowMap rm;
+  float* C2;
+  bf16* C2h;
+};
+void launch_gemm_f32(const F32GemmArgs& a, cudaStream_t s);
+
+// ---- bandwidth kernels (kernels_bw.cu)
+struct EmbedArgs {
+  const float* x;    // (rows, C, HW, HW)
+  const float* wT;   // [C*p*p, D] transposed patch-embed weight
+  const float* bias; // [D]
+  const float* pos;  // [T, D]
+  float* X;          // [rows*T, D]
+  int rows, C, img, p, D, T;
+  RowMap rm;
+};
+void launch_patch_embed(const EmbedArgs& a, cudaStream_t s);
+
+void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowMap rm, cudaStream_t s);
+
+struct NormModArgs {
+  const float* X;      // [M, D] fp32 residual stream
+  const float* w;      // [D] RMSNorm weight, or null => affine-free LayerNorm(eps 1e-6)
+  const float* mod;    // [rows, mod_ld] adaLN output
+  int mod_ld;
+  int shift_off;       // column offset of shift in mod, or -1
+  int scale_off;       // column offset of scale
+  void* out;           // [M, ldo] float or bf16
+  int ldo;
+  int M, D, T;
+  int out_bf16;
+};
+void launch_norm_modulate(const NormModArgs& a, cudaStream_t s);
+
+struct QkvPostArgs {
+  const float* qkv;  // [M, 3D] fp32 (bias already added)
+  float *q, *k, *v;  // [B, H, T, hd] fp32
+  const float *cos, *sin;      // [T, hd] or null
+  const float *qn_w, *qn_b, *kn_w, *kn_b;  // qk-norm params or null
+  int rms;           // 1: RMSNorm(eps 1e-6), 0: LayerNorm(eps 1e-5, affine)
+  int M, T, H, hd;
+};
+void launch_qkv_post_f32(const QkvPostArgs& a, cudaStream_t s);
+void launch_attention_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int T, int hd,
+                          cudaStream_t s);
+void launch_gated_residual_f32(float* X, const float* Y, const float* mod, int mod_ld, int gate_off, int M, int D,
+                               int T, cudaStream_t s);
+void launch_swiglu_f32(const float* U, float* Hh, int M, int S, int ldu, int ldh, cudaStream_t s);
+
+struct UnpatchArgs {
+  const float* Y;  // [rows*T, p*p*Cout] token-major final-linear output
+  float* out;      // (rows, Ckeep, img, img)
+  int rows, T, p, Cout, Ckeep, img;
+  RowMap rm;
+};
+void launch_unpatchify(const UnpatchArgs& a, cudaStream_t s);
+
+struct CfgArgs {
+  const float* v;    // (2n, C, HW) model output
+  float* out;        // (2n, C, HW)
+  const float* t;    // device pointer to t[0]
+  int n, C, HW;
+  float scale;
+  int interval;      // 1: guidance only when t[0] >= start
+  float start;
+  int channels;
+};
+void launch_cfg_combine(const CfgArgs& a, cudaStream_t s);
+
+// Fused CFG-combine + ODE update (Appendix A items 6-7 of SURVEY.md).
+//   stage 0 (Euler)      : x += dt * vhat
+//   stage 1 (Heun pred)  : k1 = vhat ; xp = x + dt * k1
+//   stage 2 (Heun corr)  : x += dt/2 * (k1 + vhat)
+struct OdeArgs {
+  const float* v;  // (rows, C, HW) model output of this evaluation
+  float* x;        // state (rows, C, HW)
+  float* xp;       // Heun predictor state (stage 1 output, model input of stage 2)
+  float* k1;       // Heun first-stage guided velocity
+  float* trace;    // optional: guided velocity of this evaluation, (rows, C, HW)
+  const float* t;  // device scalar: time of this evaluation
+  int rows;        // 2n under CFG, batch otherwise
+  int C, HW;
+  int use_cfg;
+  float scale;
+  int interval;
+  float start;
+  int channels;
+  float dt;
+  int stage;
+};
+void launch_ode_update(const OdeArgs& a, cudaStream_t s);
+
+void launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
+
+}  // namespace vv

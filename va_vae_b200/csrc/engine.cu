@@ -1,0 +1,846 @@
+// Engine: weights, workspace, forward / forward_with_cfg / fixed-grid ODE sampler, C ABI (include/vavae_b200.h).
+// Host logic only; every numeric op is one of the hand-written kernels in this directory.
+#include "../../include/vavae_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace vv {
+void set_attention_variant(int p_in_tmem);
+}
+using namespace vv;
+
+static thread_local std::string g_err;
+
+struct Weight {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+};
+
+struct LayerBf16 {
+  bf16 *qkv = nullptr, *proj = nullptr, *w1 = nullptr, *w2 = nullptr;  // w1: w12 (interleaved) or fc1; w2: w3 or fc2
+  float* b1 = nullptr;                                                 // interleaved w12 bias (or fc1 bias)
+};
+
+struct vavae_engine {
+  vavae_config_t cfg;
+  int device = 0;
+  // derived sizes
+  int D, T, H, hd, S, L, C, p, img, Cout, Ckeep, nmod, NM, Spad, hdp, hdv, grid_hw, Pout;
+  bool fp32;
+  bool finalized = false;
+  int chunk_rows = 0;
+  std::map<std::string, Weight> w;
+  std::vector<void*> owned;  // everything cudaMalloc'ed by the engine
+  uint64_t bytes = 0;
+  LaunchCounter counter;
+
+  // packed (both modes)
+  float* embed_wT = nullptr;  // [C*p*p, D]
+  float* ada_w = nullptr;     // fp32 mode: [NM, D]
+  float* ada_b = nullptr;     // [NM]
+  // packed (bf16 mode)
+  bf16* ada_w_h = nullptr;    // [NM, D]
+  bf16* final_w_h = nullptr;  // [Pout, D]
+  std::vector<LayerBf16> lw;
+
+  // workspace
+  float *X = nullptr, *tf = nullptr, *th = nullptr, *cbuf = nullptr, *mod = nullptr, *sc_f = nullptr;
+  bf16* sc_h = nullptr;
+  // fp32 path
+  float *A_f = nullptr, *QKV_f = nullptr, *q_f = nullptr, *k_f = nullptr, *v_f = nullptr, *O_f = nullptr, *Y_f = nullptr,
+        *U_f = nullptr, *Hh_f = nullptr, *Yfin_f = nullptr;
+  // bf16 path
+  bf16 *A_h = nullptr, *q_h = nullptr, *k_h = nullptr, *vt_h = nullptr, *O_h = nullptr, *Hh_h = nullptr;
+
+  // sampler state (lazily sized)
+  int state_rows = 0;
+  float *sx = nullptr, *sxp = nullptr, *sk1 = nullptr, *sv = nullptr, *st = nullptr;
+  int64_t* sy = nullptr;
+  float* tgrid_dev = nullptr;
+  int tgrid_cap = 0;
+
+  template <typename Tp>
+  Tp* alloc(size_t n, bool zero = false) {
+    void* ptr = nullptr;
+    size_t b = n * sizeof(Tp);
+    if (b == 0) b = sizeof(Tp);
+    VV_CUDA(cudaMalloc(&ptr, b));
+    if (zero) VV_CUDA(cudaMemset(ptr, 0, b));
+    owned.push_back(ptr);
+    bytes += b;
+    return reinterpret_cast<Tp*>(ptr);
+  }
+  void release(void* ptr) {
+    for (auto& o : owned)
+      if (o == ptr && ptr) {
+        cudaFree(ptr);
+        o = nullptr;
+      }
+  }
+  const Weight& W(const std::string& name) const {
+    auto it = w.find(name);
+    if (it == w.end()) throw Error("missing weight: " + name);
+    return it->second;
+  }
+  const Weight& W(const std::string& name, std::initializer_list<int64_t> shape) const {
+    const Weight& x = W(name);
+    std::vector<int64_t> s(shape);
+    if (x.shape != s) {
+      std::string got, want;
+      for (auto v : x.shape) got += std::to_string(v) + ",";
+      for (auto v : s) want += std::to_string(v) + ",";
+      throw Error("weight " + name + " has shape (" + got + ") expected (" + want + ")");
+    }
+    return x;
+  }
+  bool has(const std::string& name) const { return w.count(name) != 0; }
+};
+
+// --------------------------------------------------------------------------------------------- helpers
+static std::string blk(int i, const char* s) { return "blocks." + std::to_string(i) + "." + s; }
+
+__global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int r = idx / cols, c = idx % cols;
+  out[(size_t)c * rows + r] = in[idx];
+}
+// w12 rows interleaved: out row 2j = in row j (x1, gated), 2j+1 = in row S+j (x2); K pitch ldo
+__global__ void k_pack_rows_bf16(const float* __restrict__ in, bf16* __restrict__ out, int rows, int K, int ldo,
+                                 int interleave_S) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * K) return;
+  int r = (int)(idx / K), c = (int)(idx % K);
+  int src = r;
+  if (interleave_S > 0) src = (r & 1) ? interleave_S + (r >> 1) : (r >> 1);
+  out[(size_t)r * ldo + c] = __float2bfloat16_rn(in[(size_t)src * K + c]);
+}
+__global__ void k_interleave_bias(const float* __restrict__ in, float* __restrict__ out, int S) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= 2 * S) return;
+  out[r] = in[(r & 1) ? S + (r >> 1) : (r >> 1)];
+}
+__global__ void k_set_scalar(float* dst, const float* src, int idx) { dst[0] = src[idx]; }
+
+static void pack_bf16(vavae_engine* e, const float* src, bf16* dst, int rows, int K, int ldo, int interleave_S,
+                      cudaStream_t s) {
+  size_t total = (size_t)rows * K;
+  k_pack_rows_bf16<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, rows, K, ldo, interleave_S);
+  VV_LAUNCH_CHECK();
+}
+
+static void derive(vavae_engine* e) {
+  const vavae_config_t& c = e->cfg;
+  VV_CHECK(c.abi_version == VAVAE_ABI_VERSION, "vavae_config_t.abi_version mismatch");
+  VV_CHECK(c.patch_size >= 1 && c.input_size % c.patch_size == 0, "input_size must be divisible by patch_size");
+  VV_CHECK(c.hidden_size % c.num_heads == 0, "dim should be divisible by num_heads");  // lightningdit.py:49
+  e->D = c.hidden_size;
+  e->H = c.num_heads;
+  e->hd = e->D / e->H;
+  e->L = c.depth;
+  e->C = c.in_channels;
+  e->p = c.patch_size;
+  e->img = c.input_size;
+  e->grid_hw = c.input_size / c.patch_size;
+  e->T = e->grid_hw * e->grid_hw;
+  e->S = c.mlp_hidden;
+  e->Cout = c.learn_sigma ? 2 * c.in_channels : c.in_channels;
+  e->Ckeep = c.in_channels;
+  e->Pout = e->p * e->p * e->Cout;
+  e->nmod = c.wo_shift ? 4 : 6;
+  e->NM = e->L * e->nmod * e->D + 2 * e->D;
+  e->Spad = ((e->S + 7) / 8) * 8;
+  e->hdp = ((e->hd + 15) / 16) * 16;
+  e->hdv = ((e->hd + 15) / 16) * 16;
+  e->fp32 = c.precision == VAVAE_PREC_FP32;
+  VV_CHECK(c.precision == VAVAE_PREC_FP32 || c.precision == VAVAE_PREC_BF16, "unknown precision mode");
+  VV_CHECK(e->D % 4 == 0 && e->D <= 2048, "hidden_size must be a multiple of 4 and <= 2048");
+  VV_CHECK(e->hd % 2 == 0, "head_dim must be even (RoPE pairs)");
+  VV_CHECK((e->img * e->img) % 4 == 0, "latent H*W must be a multiple of 4");
+  if (!e->fp32) {
+    VV_CHECK(e->D % 16 == 0 && e->hd % 8 == 0 && e->hd <= 128, "bf16 path: hidden % 16, head_dim % 8, head_dim <= 128");
+    VV_CHECK(e->T % 8 == 0, "bf16 path: token count must be a multiple of 8");
+    VV_CHECK(e->S % 2 == 0, "bf16 path: mlp hidden must be even");
+  }
+}
+
+// --------------------------------------------------------------------------------------------- finalize
+static void finalize(vavae_engine* e, cudaStream_t s) {
+  const int D = e->D, L = e->L, S = e->S, C = e->C, p = e->p, T = e->T, hd = e->hd;
+  const vavae_config_t& c = e->cfg;
+  // ---- presence / shape validation of the reference state_dict
+  e->W("pos_embed", {1, T, D});
+  e->W("x_embedder.proj.weight", {D, C, p, p});
+  e->W("x_embedder.proj.bias", {D});
+  e->W("t_embedder.mlp.0.weight", {D, 256});
+  e->W("t_embedder.mlp.0.bias", {D});
+  e->W("t_embedder.mlp.2.weight", {D, D});
+  e->W("t_embedder.mlp.2.bias", {D});
+  e->W("t_embedder.freqs", {128});
+  e->W("y_embedder.embedding_table.weight", {c.label_rows, D});
+  if (c.use_rope) {
+    e->W("feat_rope.freqs_cos", {T, hd});
+    e->W("feat_rope.freqs_sin", {T, hd});
+  }
+  for (int i = 0; i < L; ++i) {
+    if (c.use_rmsnorm) {
+      e->W(blk(i, "norm1.weight"), {D});
+      e->W(blk(i, "norm2.weight"), {D});
+    }
+    e->W(blk(i, "attn.qkv.weight"), {3 * D, D});
+    e->W(blk(i, "attn.qkv.bias"), {3 * D});
+    if (c.use_qknorm) {
+      e->W(blk(i, "attn.q_norm.weight"), {hd});
+      e->W(blk(i, "attn.k_norm.weight"), {hd});
+      if (!c.use_rmsnorm) {
+        e->W(blk(i, "attn.q_norm.bias"), {hd});
+        e->W(blk(i, "attn.k_norm.bias"), {hd});
+      }
+    }
+    e->W(blk(i, "attn.proj.weight"), {D, D});
+    e->W(blk(i, "attn.proj.bias"), {D});
+    if (c.use_swiglu) {
+      e->W(blk(i, "mlp.w12.weight"), {2 * S, D});
+      e->W(blk(i, "mlp.w12.bias"), {2 * S});
+      e->W(blk(i, "mlp.w3.weight"), {D, S});
+      e->W(blk(i, "mlp.w3.bias"), {D});
+    } else {
+      e->W(blk(i, "mlp.fc1.weight"), {S, D});
+      e->W(blk(i, "mlp.fc1.bias"), {S});
+      e->W(blk(i, "mlp.fc2.weight"), {D, S});
+      e->W(blk(i, "mlp.fc2.bias"), {D});
+    }
+    e->W(blk(i, "adaLN_modulation.1.weight"), {e->nmod * D, D});
+    e->W(blk(i, "adaLN_modulation.1.bias"), {e->nmod * D});
+  }
+  if (c.use_rmsnorm) e->W("final_layer.norm_final.weight", {D});
+  e->W("final_layer.linear.weight", {e->Pout, D});
+  e->W("final_layer.linear.bias", {e->Pout});
+  e->W("final_layer.adaLN_modulation.1.weight", {2 * D, D});
+  e->W("final_layer.adaLN_modulation.1.bias", {2 * D});
+
+  // ---- packing shared by both modes
+  const int Cpp = C * p * p;
+  e->embed_wT = e->alloc<float>((size_t)Cpp * D);
+  k_transpose<<<cdiv(D * Cpp, 256), 256, 0, s>>>(e->W("x_embedder.proj.weight").d, e->embed_wT, D, Cpp);
+  VV_LAUNCH_CHECK();
+  // batched adaLN: one [NM, D] matrix = every block's modulation Linear followed by the final layer's
+  e->ada_b = e->alloc<float>(e->NM);
+  if (e->fp32) e->ada_w = e->alloc<float>((size_t)e->NM * D);
+  else e->ada_w_h = e->alloc<bf16>((size_t)e->NM * D);
+  for (int i = 0; i <= L; ++i) {
+    const bool fin = i == L;
+    const Weight& aw = e->W(fin ? std::string("final_layer.adaLN_modulation.1.weight") : blk(i, "adaLN_modulation.1.weight"));
+    const Weight& ab = e->W(fin ? std::string("final_layer.adaLN_modulation.1.bias") : blk(i, "adaLN_modulation.1.bias"));
+    const size_t row0 = (size_t)i * e->nmod * D;
+    const int rows = fin ? 2 * D : e->nmod * D;
+    VV_CUDA(cudaMemcpyAsync(e->ada_b + row0, ab.d, (size_t)rows * 4, cudaMemcpyDeviceToDevice, s));
+    if (e->fp32) VV_CUDA(cudaMemcpyAsync(e->ada_w + row0 * D, aw.d, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, s));
+    else pack_bf16(e, aw.d, e->ada_w_h + row0 * D, rows, D, D, 0, s);
+  }
+  if (!e->fp32) {
+    e->lw.resize(L);
+    for (int i = 0; i < L; ++i) {
+      LayerBf16& lw = e->lw[i];
+      lw.qkv = e->alloc<bf16>((size_t)3 * D * D);
+      pack_bf16(e, e->W(blk(i, "attn.qkv.weight")).d, lw.qkv, 3 * D, D, D, 0, s);
+      lw.proj = e->alloc<bf16>((size_t)D * D);
+      pack_bf16(e, e->W(blk(i, "attn.proj.weight")).d, lw.proj, D, D, D, 0, s);
+      if (c.use_swiglu) {
+        lw.w1 = e->alloc<bf16>((size_t)2 * S * D);
+        pack_bf16(e, e->W(blk(i, "mlp.w12.weight")).d, lw.w1, 2 * S, D, D, S, s);
+        lw.b1 = e->alloc<float>(2 * S);
+        k_interleave_bias<<<cdiv(2 * S, 256), 256, 0, s>>>(e->W(blk(i, "mlp.w12.bias")).d, lw.b1, S);
+        VV_LAUNCH_CHECK();
+        lw.w2 = e->alloc<bf16>((size_t)D * e->Spad, true);
+        pack_bf16(e, e->W(blk(i, "mlp.w3.weight")).d, lw.w2, D, S, e->Spad, 0, s);
+      } else {
+        lw.w1 = e->alloc<bf16>((size_t)S * D);
+        pack_bf16(e, e->W(blk(i, "mlp.fc1.weight")).d, lw.w1, S, D, D, 0, s);
+        lw.b1 = e->W(blk(i, "mlp.fc1.bias")).d;
+        lw.w2 = e->alloc<bf16>((size_t)D * e->Spad, true);
+        pack_bf16(e, e->W(blk(i, "mlp.fc2.weight")).d, lw.w2, D, S, e->Spad, 0, s);
+      }
+    }
+    e->final_w_h = e->alloc<bf16>((size_t)e->Pout * D);
+    pack_bf16(e, e->W("final_layer.linear.weight").d, e->final_w_h, e->Pout, D, D, 0, s);
+    VV_CUDA(cudaStreamSynchronize(s));
+    // the fp32 originals of the big matrices are no longer needed on the bf16 path
+    for (int i = 0; i < L; ++i) {
+      std::vector<std::string> big = {"attn.qkv.weight", "attn.proj.weight", "adaLN_modulation.1.weight"};
+      if (c.use_swiglu) { big.push_back("mlp.w12.weight"); big.push_back("mlp.w3.weight"); }
+      else { big.push_back("mlp.fc1.weight"); big.push_back("mlp.fc2.weight"); }
+      for (auto& nme : big) {
+        Weight& x = e->w[blk(i, nme.c_str())];
+        e->release(x.d);
+        e->bytes -= x.numel * 4;
+        x.d = nullptr;
+      }
+    }
+  }
+
+  // ---- workspace
+  int R = c.max_chunk_rows > 0 ? c.max_chunk_rows : (e->fp32 ? 16 : 128);
+  if (R % 2) R += 1;
+  e->chunk_rows = R;
+  const size_t M = (size_t)R * T;
+  e->X = e->alloc<float>(M * D);
+  e->tf = e->alloc<float>((size_t)R * 256);
+  e->th = e->alloc<float>((size_t)R * D);
+  e->cbuf = e->alloc<float>((size_t)R * D);
+  e->mod = e->alloc<float>((size_t)R * e->NM);
+  e->st = e->alloc<float>(4);
+  if (e->fp32) {
+    e->sc_f = e->alloc<float>((size_t)R * D);
+    e->A_f = e->alloc<float>(M * D);
+    e->QKV_f = e->alloc<float>(M * 3 * D);
+    e->q_f = e->alloc<float>(M * D);
+    e->k_f = e->alloc<float>(M * D);
+    e->v_f = e->alloc<float>(M * D);
+    e->O_f = e->alloc<float>(M * D);
+    e->Y_f = e->alloc<float>(M * D);
+    if (c.use_swiglu) e->U_f = e->alloc<float>(M * 2 * S);
+    e->Hh_f = e->alloc<float>(M * S);
+    e->Yfin_f = e->alloc<float>(M * e->Pout);
+  } else {
+    e->sc_h = e->alloc<bf16>((size_t)R * D);
+    e->A_h = e->alloc<bf16>(M * D);
+    // padding columns d in [hd, hdp) of q/k and rows [hd, hdv) of v^T stay zero forever (never written)
+    e->q_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
+    e->k_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
+    e->vt_h = e->alloc<bf16>((size_t)R * e->H * e->hdv * T, true);
+    e->O_h = e->alloc<bf16>(M * D);
+    e->Hh_h = e->alloc<bf16>(M * e->Spad, true);
+  }
+  VV_CUDA(cudaStreamSynchronize(s));
+  e->finalized = true;
+}
+
+// --------------------------------------------------------------------------------------------- forward (one chunk)
+struct ModOff {
+  int shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp;
+};
+static ModOff mod_offsets(const vavae_engine* e, int layer) {
+  const int D = e->D, base = layer * e->nmod * D;
+  ModOff o;
+  if (e->cfg.wo_shift) {  // lightningdit.py:242-244
+    o.shift_msa = -1; o.scale_msa = base; o.gate_msa = base + D;
+    o.shift_mlp = -1; o.scale_mlp = base + 2 * D; o.gate_mlp = base + 3 * D;
+  } else {  // lightningdit.py:246
+    o.shift_msa = base; o.scale_msa = base + D; o.gate_msa = base + 2 * D;
+    o.shift_mlp = base + 3 * D; o.scale_mlp = base + 4 * D; o.gate_mlp = base + 5 * D;
+  }
+  return o;
+}
+
+static void norm_mod(vavae_engine* e, const float* w, int shift_off, int scale_off, int M, cudaStream_t s) {
+  NormModArgs n;
+  n.X = e->X; n.w = w; n.mod = e->mod; n.mod_ld = e->NM; n.shift_off = shift_off; n.scale_off = scale_off;
+  n.out = e->fp32 ? (void*)e->A_f : (void*)e->A_h; n.ldo = e->D; n.M = M; n.D = e->D; n.T = e->T;
+  n.out_bf16 = e->fp32 ? 0 : 1;
+  launch_norm_modulate(n, s);
+}
+
+static void gemm32(const float* A, int lda, const float* Wt, const float* bias, float* Cc, int ldc, int M, int N, int K,
+                   int epi, cudaStream_t s) {
+  F32GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.W = Wt; g.ldw = K; g.bias = bias; g.C = Cc; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.epi = epi;
+  launch_gemm_f32(g, s);
+}
+
+static TcGemmArgs tc_args(const bf16* A, int lda, const bf16* Wt, int ldw, int M, int N, int K, int epi,
+                          const float* bias) {
+  TcGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.W = Wt; g.ldw = ldw; g.M = M; g.N = N; g.K = K; g.epi = epi; g.bias = bias;
+  return g;
+}
+
+static void conditioning(vavae_engine* e, int rows, const RowMap& rm, const float* t, const int64_t* y, cudaStream_t s) {
+  const int D = e->D;
+  launch_tfreq(t, e->W("t_embedder.freqs").d, e->tf, rows, rm, s);
+  gemm32(e->tf, 256, e->W("t_embedder.mlp.0.weight").d, e->W("t_embedder.mlp.0.bias").d, e->th, D, rows, D, 256,
+         F32_EPI_SILU, s);
+  F32GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = e->th; g.lda = D; g.W = e->W("t_embedder.mlp.2.weight").d; g.ldw = D; g.bias = e->W("t_embedder.mlp.2.bias").d;
+  g.C = e->cbuf; g.ldc = D; g.M = rows; g.N = D; g.K = D; g.epi = F32_EPI_ADD_LABEL_SILU;
+  g.table = e->W("y_embedder.embedding_table.weight").d; g.labels = y; g.rm = rm;
+  g.C2 = e->fp32 ? e->sc_f : nullptr; g.C2h = e->fp32 ? nullptr : e->sc_h;
+  launch_gemm_f32(g, s);
+  // every adaLN modulation of the network in one GEMM: mod[rows, NM]
+  if (e->fp32) {
+    gemm32(e->sc_f, D, e->ada_w, e->ada_b, e->mod, e->NM, rows, e->NM, D, F32_EPI_NONE, s);
+  } else {
+    TcGemmArgs a = tc_args(e->sc_h, D, e->ada_w_h, D, rows, e->NM, D, TC_EPI_BIAS_F32, e->ada_b);
+    a.out = e->mod; a.ldo = e->NM;
+    launch_gemm_tc(a, s);
+  }
+}
+
+static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const float* x, const float* t, const int64_t* y,
+                          float* out, cudaStream_t s) {
+  const int D = e->D, T = e->T, H = e->H, hd = e->hd, S = e->S, L = e->L;
+  const int M = rows * T;
+  const vavae_config_t& c = e->cfg;
+  VV_CHECK(rows <= e->chunk_rows, "forward_chunk: chunk larger than workspace");
+  EmbedArgs ea;
+  ea.x = x; ea.wT = e->embed_wT; ea.bias = e->W("x_embedder.proj.bias").d; ea.pos = e->W("pos_embed").d; ea.X = e->X;
+  ea.rows = rows; ea.C = e->C; ea.img = e->img; ea.p = e->p; ea.D = D; ea.T = T; ea.rm = rm;
+  launch_patch_embed(ea, s);
+  conditioning(e, rows, rm, t, y, s);
+  const float* rcos = c.use_rope ? e->W("feat_rope.freqs_cos").d : nullptr;
+  const float* rsin = c.use_rope ? e->W("feat_rope.freqs_sin").d : nullptr;
+
+  for (int i = 0; i < L; ++i) {
+    const ModOff mo = mod_offsets(e, i);
+    const float* n1 = c.use_rmsnorm ? e->W(blk(i, "norm1.weight")).d : nullptr;
+    const float* n2 = c.use_rmsnorm ? e->W(blk(i, "norm2.weight")).d : nullptr;
+    const float *qnw = nullptr, *qnb = nullptr, *knw = nullptr, *knb = nullptr;
+    if (c.use_qknorm) {
+      qnw = e->W(blk(i, "attn.q_norm.weight")).d;
+      knw = e->W(blk(i, "attn.k_norm.weight")).d;
+      if (!c.use_rmsnorm) {
+        qnb = e->W(blk(i, "attn.q_norm.bias")).d;
+        knb = e->W(blk(i, "attn.k_norm.bias")).d;
+      }
+    }
+    // ---- attention branch
+    norm_mod(e, n1, mo.shift_msa, mo.scale_msa, M, s);
+    if (e->fp32) {
+      gemm32(e->A_f, D, e->W(blk(i, "attn.qkv.weight")).d, e->W(blk(i, "attn.qkv.bias")).d, e->QKV_f, 3 * D, M, 3 * D, D,
+             F32_EPI_NONE, s);
+      QkvPostArgs qa;
+      qa.qkv = e->QKV_f; qa.q = e->q_f; qa.k = e->k_f; qa.v = e->v_f; qa.cos = rcos; qa.sin = rsin;
+      qa.qn_w = qnw; qa.qn_b = qnb; qa.kn_w = knw; qa.kn_b = knb; qa.rms = c.use_rmsnorm; qa.M = M; qa.T = T; qa.H = H;
+      qa.hd = hd;
+      launch_qkv_post_f32(qa, s);
+      launch_attention_f32(e->q_f, e->k_f, e->v_f, e->O_f, rows, H, T, hd, s);
+      gemm32(e->O_f, D, e->W(blk(i, "attn.proj.weight")).d, e->W(blk(i, "attn.proj.bias")).d, e->Y_f, D, M, D, D,
+             F32_EPI_NONE, s);
+      launch_gated_residual_f32(e->X, e->Y_f, e->mod, e->NM, mo.gate_msa, M, D, T, s);
+    } else {
+      TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].qkv, D, M, 3 * D, D, TC_EPI_QKV, e->W(blk(i, "attn.qkv.bias")).d);
+      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
+      a.kn_b = knb; a.qk_rms = c.use_rmsnorm; a.H = H; a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
+      launch_gemm_tc(a, s);
+      TcAttnArgs at;
+      at.q = e->q_h; at.k = e->k_h; at.vt = e->vt_h; at.out = e->O_h; at.B = rows; at.H = H; at.T = T; at.hd = hd;
+      at.hdp = e->hdp; at.hdv = e->hdv;
+      launch_attention_tc(at, s);
+      TcGemmArgs pr = tc_args(e->O_h, D, e->lw[i].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(i, "attn.proj.bias")).d);
+      pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NM; pr.gate_off = mo.gate_msa; pr.T = T;
+      launch_gemm_tc(pr, s);
+    }
+    // ---- MLP branch
+    norm_mod(e, n2, mo.shift_mlp, mo.scale_mlp, M, s);
+    if (e->fp32) {
+      if (c.use_swiglu) {
+        gemm32(e->A_f, D, e->W(blk(i, "mlp.w12.weight")).d, e->W(blk(i, "mlp.w12.bias")).d, e->U_f, 2 * S, M, 2 * S, D,
+               F32_EPI_NONE, s);
+        launch_swiglu_f32(e->U_f, e->Hh_f, M, S, 2 * S, S, s);
+        gemm32(e->Hh_f, S, e->W(blk(i, "mlp.w3.weight")).d, e->W(blk(i, "mlp.w3.bias")).d, e->Y_f, D, M, D, S,
+               F32_EPI_NONE, s);
+      } else {
+        gemm32(e->A_f, D, e->W(blk(i, "mlp.fc1.weight")).d, e->W(blk(i, "mlp.fc1.bias")).d, e->Hh_f, S, M, S, D,
+               F32_EPI_GELU_TANH, s);
+        gemm32(e->Hh_f, S, e->W(blk(i, "mlp.fc2.weight")).d, e->W(blk(i, "mlp.fc2.bias")).d, e->Y_f, D, M, D, S,
+               F32_EPI_NONE, s);
+      }
+      launch_gated_residual_f32(e->X, e->Y_f, e->mod, e->NM, mo.gate_mlp, M, D, T, s);
+    } else {
+      if (c.use_swiglu) {
+        TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, 2 * S, D, TC_EPI_SWIGLU, e->lw[i].b1);
+        a.out = e->Hh_h; a.ldo = e->Spad;
+        launch_gemm_tc(a, s);
+      } else {
+        TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, S, D, TC_EPI_GELU_BF16, e->lw[i].b1);
+        a.out = e->Hh_h; a.ldo = e->Spad;
+        launch_gemm_tc(a, s);
+      }
+      const float* b2 = e->W(blk(i, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d;
+      TcGemmArgs a = tc_args(e->Hh_h, e->Spad, e->lw[i].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL, b2);
+      a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NM; a.gate_off = mo.gate_mlp; a.T = T;
+      launch_gemm_tc(a, s);
+    }
+  }
+  // ---- final layer (lightningdit.py:267-272): shift first, then scale
+  const int fbase = L * e->nmod * D;
+  norm_mod(e, c.use_rmsnorm ? e->W("final_layer.norm_final.weight").d : nullptr, fbase, fbase + D, M, s);
+  if (e->fp32) {
+    gemm32(e->A_f, D, e->W("final_layer.linear.weight").d, e->W("final_layer.linear.bias").d, e->Yfin_f, e->Pout, M,
+           e->Pout, D, F32_EPI_NONE, s);
+    UnpatchArgs u;
+    u.Y = e->Yfin_f; u.out = out; u.rows = rows; u.T = T; u.p = e->p; u.Cout = e->Cout; u.Ckeep = e->Ckeep; u.img = e->img;
+    u.rm = rm;
+    launch_unpatchify(u, s);
+  } else {
+    TcGemmArgs a = tc_args(e->A_h, D, e->final_w_h, D, M, e->Pout, D, TC_EPI_FINAL, e->W("final_layer.linear.bias").d);
+    a.out = out; a.T = T; a.p = e->p; a.Cout = e->Cout; a.Ckeep = e->Ckeep; a.img = e->img; a.rm = rm;
+    launch_gemm_tc(a, s);
+  }
+}
+
+// forward over `batch` independent rows (no CFG pairing)
+static void forward_plain(vavae_engine* e, const float* x, const float* t, int t_stride, const int64_t* y, float* out,
+                          int batch, cudaStream_t s) {
+  for (int r0 = 0; r0 < batch; r0 += e->chunk_rows) {
+    const int rows = std::min(e->chunk_rows, batch - r0);
+    RowMap rm;
+    rm.seg_rows = rows;
+    rm.x_off[0] = rm.x_off[1] = r0;
+    rm.y_off[0] = rm.y_off[1] = r0;
+    rm.t_off[0] = rm.t_off[1] = r0;
+    rm.out_off[0] = rm.out_off[1] = r0;
+    rm.t_stride = t_stride;
+    forward_chunk(e, rows, rm, x, t, y, out, s);
+  }
+}
+// forward of [half, half] (lightningdit.py:425-427): model row b<n and b+n both read latent row b
+static void forward_pairs(vavae_engine* e, const float* x, const float* t, int t_stride, const int64_t* y, float* out,
+                          int n, cudaStream_t s) {
+  const int per = e->chunk_rows / 2;
+  for (int s0 = 0; s0 < n; s0 += per) {
+    const int m = std::min(per, n - s0);
+    RowMap rm;
+    rm.seg_rows = m;
+    rm.x_off[0] = s0; rm.x_off[1] = s0;
+    rm.y_off[0] = s0; rm.y_off[1] = n + s0;
+    rm.t_off[0] = s0; rm.t_off[1] = n + s0;
+    rm.out_off[0] = s0; rm.out_off[1] = n + s0;
+    rm.t_stride = t_stride;
+    forward_chunk(e, 2 * m, rm, x, t, y, out, s);
+  }
+}
+
+static void ensure_state(vavae_engine* e, int rows) {
+  if (rows <= e->state_rows) return;
+  const size_t per = (size_t)e->C * e->img * e->img;
+  for (float** pp : {&e->sx, &e->sxp, &e->sk1, &e->sv}) {
+    if (*pp) e->release(*pp);
+    *pp = e->alloc<float>((size_t)rows * per);
+  }
+  if (e->sy) e->release(e->sy);
+  e->sy = e->alloc<int64_t>(rows);
+  e->state_rows = rows;
+}
+
+static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const float* t_grid, int n_points, int method,
+                       int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start, int cfg_channels,
+                       float* out_final, float* out_trace, int batch, cudaStream_t s) {
+  VV_CHECK(n_points >= 2, "sample_ode: need at least two grid points");
+  VV_CHECK(method == VAVAE_ODE_EULER || method == VAVAE_ODE_HEUN, "sample_ode: method must be euler or heun (fixed grid)");
+  VV_CHECK(!use_cfg || batch % 2 == 0, "sample_ode: CFG batch must be even (inference.py:205-211)");
+  for (int j = 0; j + 1 < n_points; ++j) VV_CHECK(t_grid[j] < t_grid[j + 1], "ODE sampler has to be in forward time");
+  ensure_state(e, batch);
+  if (n_points > e->tgrid_cap) {
+    if (e->tgrid_dev) e->release(e->tgrid_dev);
+    e->tgrid_dev = e->alloc<float>(n_points);
+    e->tgrid_cap = n_points;
+  }
+  const size_t per = (size_t)e->C * e->img * e->img;
+  const size_t state_bytes = (size_t)batch * per * sizeof(float);
+  VV_CUDA(cudaMemcpyAsync(e->tgrid_dev, t_grid, (size_t)n_points * sizeof(float), cudaMemcpyHostToDevice, s));
+  float* xs = out_final;  // integrate in place in the caller's output buffer
+  if (xs != z) VV_CUDA(cudaMemcpyAsync(xs, z, state_bytes, cudaMemcpyDeviceToDevice, s));
+  int eval = 0;
+  auto eval_model = [&](const float* xin, int tidx) {
+    const float* tp = e->tgrid_dev + tidx;  // every row uses the same time: t_stride = 0
+    if (use_cfg) forward_pairs(e, xin, tp, 0, y, e->sv, batch / 2, s);
+    else forward_plain(e, xin, tp, 0, y, e->sv, batch, s);
+  };
+  OdeArgs o;
+  o.v = e->sv; o.x = xs; o.xp = e->sxp; o.k1 = e->sk1; o.rows = batch; o.C = e->C; o.HW = e->img * e->img;
+  o.use_cfg = use_cfg; o.scale = cfg_scale; o.interval = cfg_interval; o.start = cfg_interval_start;
+  o.channels = cfg_channels;
+  for (int j = 0; j + 1 < n_points; ++j) {
+    const float dt = t_grid[j + 1] - t_grid[j];  // fp32, like torchdiffeq's t1 - t0 on fp32 tensors
+    o.dt = dt;
+    eval_model(xs, j);
+    o.t = e->tgrid_dev + j;
+    o.trace = out_trace ? out_trace + (size_t)(eval++) * batch * per : nullptr;
+    o.stage = method == VAVAE_ODE_EULER ? 0 : 1;
+    launch_ode_update(o, s);
+    if (method == VAVAE_ODE_HEUN) {
+      eval_model(e->sxp, j + 1);
+      o.t = e->tgrid_dev + j + 1;
+      o.trace = out_trace ? out_trace + (size_t)(eval++) * batch * per : nullptr;
+      o.stage = 2;
+      launch_ode_update(o, s);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------- C ABI
+#define VV_API_BEGIN(e)                 \
+  try {                                 \
+    vv::g_counter = (e) ? &(e)->counter : nullptr; \
+    if (e) VV_CUDA(cudaSetDevice((e)->device));
+#define VV_API_END()                    \
+    return 0;                           \
+  } catch (const std::exception& ex) {  \
+    g_err = ex.what();                  \
+    return 1;                           \
+  }
+
+extern "C" {
+
+int vavae_abi_version(void) { return VAVAE_ABI_VERSION; }
+const char* vavae_last_error(void) { return g_err.c_str(); }
+
+int vavae_create(const vavae_config_t* cfg, int device, vavae_engine_t** out) {
+  vavae_engine* e = nullptr;
+  try {
+    VV_CHECK(cfg && out, "null argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+      throw Error("no CUDA device available: this engine has no CPU fallback (" + std::string(cudaGetErrorString(ce)) + ")");
+    VV_CHECK(device >= 0 && device < ndev, "device index out of range");
+    VV_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VV_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw Error("this engine is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor));
+    e = new vavae_engine();
+    e->cfg = *cfg;
+    e->device = device;
+    derive(e);
+    *out = e;
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    delete e;
+    return 1;
+  }
+}
+
+int vavae_destroy(vavae_engine_t* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (void* p : e->owned)
+    if (p) cudaFree(p);
+  delete e;
+  return 0;
+}
+
+int vavae_load_weight(vavae_engine_t* e, const char* name, const float* data, const int64_t* shape, int ndim,
+                      int is_device) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && name && data && shape && ndim >= 1, "null argument");
+  VV_CHECK(!e->finalized, "load_weight after finalize");
+  Weight wt;
+  wt.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    wt.shape.push_back(shape[i]);
+    wt.numel *= (size_t)shape[i];
+  }
+  auto it = e->w.find(name);
+  if (it != e->w.end()) {
+    VV_CHECK(it->second.numel == wt.numel, std::string("reloaded weight changes size: ") + name);
+    wt.d = it->second.d;
+  } else {
+    wt.d = e->alloc<float>(wt.numel);
+  }
+  VV_CUDA(cudaMemcpy(wt.d, data, wt.numel * sizeof(float), is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  e->w[name] = wt;
+  VV_API_END()
+}
+
+int vavae_finalize(vavae_engine_t* e, void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && !e->finalized, "finalize called twice");
+  finalize(e, (cudaStream_t)stream);
+  VV_API_END()
+}
+
+int vavae_forward(vavae_engine_t* e, const float* x, const float* t, const int64_t* y, float* out, int batch,
+                  void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && e->finalized, "engine not finalized");
+  VV_CHECK(batch > 0, "empty batch");
+  forward_plain(e, x, t, 1, y, out, batch, (cudaStream_t)stream);
+  VV_API_END()
+}
+
+int vavae_forward_with_cfg(vavae_engine_t* e, const float* x, const float* t, const int64_t* y, float cfg_scale,
+                           int cfg_interval, float cfg_interval_start, int cfg_channels, float* out, int batch,
+                           void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && e->finalized, "engine not finalized");
+  VV_CHECK(batch > 0 && batch % 2 == 0, "forward_with_cfg needs an even batch (cond rows then null-label rows)");
+  cudaStream_t s = (cudaStream_t)stream;
+  ensure_state(e, batch);
+  forward_pairs(e, x, t, 1, y, e->sv, batch / 2, s);
+  CfgArgs c;
+  c.v = e->sv; c.out = out; c.t = t; c.n = batch / 2; c.C = e->C; c.HW = e->img * e->img; c.scale = cfg_scale;
+  c.interval = cfg_interval; c.start = cfg_interval_start; c.channels = cfg_channels;
+  launch_cfg_combine(c, s);
+  VV_API_END()
+}
+
+int vavae_sample_ode(vavae_engine_t* e, const float* z, const int64_t* y, const float* t_grid, int n_points, int method,
+                     int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start, int cfg_channels,
+                     float* out_final, float* out_trace, int batch, void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && e->finalized, "engine not finalized");
+  VV_CHECK(batch > 0 && z && y && t_grid && out_final, "null / empty argument");
+  sample_ode(e, z, y, t_grid, n_points, method, use_cfg, cfg_scale, cfg_interval, cfg_interval_start, cfg_channels,
+             out_final, out_trace, batch, (cudaStream_t)stream);
+  VV_API_END()
+}
+
+int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t* y_host, const float* t_grid,
+                          int n_points, int method, int use_cfg, float cfg_scale, int cfg_interval,
+                          float cfg_interval_start, int cfg_channels, float* out_final_host, int batch, void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && e->finalized, "engine not finalized");
+  VV_CHECK(batch > 0 && z_host && y_host && t_grid && out_final_host, "null / empty argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ensure_state(e, batch);
+  const size_t bytes = (size_t)batch * e->C * e->img * e->img * sizeof(float);
+  VV_CUDA(cudaMemcpyAsync(e->sx, z_host, bytes, cudaMemcpyHostToDevice, s));
+  VV_CUDA(cudaMemcpyAsync(e->sy, y_host, (size_t)batch * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  sample_ode(e, e->sx, e->sy, t_grid, n_points, method, use_cfg, cfg_scale, cfg_interval, cfg_interval_start,
+             cfg_channels, e->sx, nullptr, batch, s);
+  VV_CUDA(cudaMemcpyAsync(out_final_host, e->sx, bytes, cudaMemcpyDeviceToHost, s));
+  VV_CUDA(cudaStreamSynchronize(s));
+  VV_API_END()
+}
+
+uint64_t vavae_launch_count(const vavae_engine_t* e) { return e ? e->counter.n : 0; }
+uint64_t vavae_device_bytes(const vavae_engine_t* e) { return e ? e->bytes : 0; }
+
+// ---- kernel-level test entry points -----------------------------------------------------------
+int vavae_test_gemm_bf16(const void* A, const void* Wt, const float* bias, float* Cc, int M, int N, int K, void* stream) {
+  try {
+    vv::g_counter = nullptr;
+    TcGemmArgs a = tc_args((const bf16*)A, K, (const bf16*)Wt, K, M, N, K, TC_EPI_BIAS_F32, bias);
+    a.out = Cc;
+    a.ldo = N;
+    launch_gemm_tc(a, (cudaStream_t)stream);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return 1;
+  }
+}
+
+int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int T, int hd,
+                              void* stream) {
+  try {
+    vv::g_counter = nullptr;
+    TcAttnArgs a;
+    a.q = (const bf16*)q; a.k = (const bf16*)k; a.vt = (const bf16*)vt; a.out = (bf16*)out;
+    a.B = B; a.H = H; a.T = T; a.hd = hd; a.hdp = ((hd + 15) / 16) * 16; a.hdv = a.hdp;
+    launch_attention_tc(a, (cudaStream_t)stream);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return 1;
+  }
+}
+
+int vavae_set_attention_variant(int p_in_tmem) {
+  vv::set_attention_variant(p_in_tmem);
+  return 0;
+}
+
+int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work, void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && e->finalized && kernel && ms && work, "bad argument");
+  VV_CHECK(rows > 0 && rows <= e->chunk_rows, "time_kernel: rows must fit the engine's chunk");
+  VV_CHECK(!e->fp32, "time_kernel measures the bf16 production kernels");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = e->D, T = e->T, S = e->S, H = e->H, hd = e->hd, M = rows * T;
+  const ModOff mo = mod_offsets(e, 0);
+  const vavae_config_t& c = e->cfg;
+  std::string k = kernel;
+  std::function<void()> fn;
+  const float* rcos = c.use_rope ? e->W("feat_rope.freqs_cos").d : nullptr;
+  const float* rsin = c.use_rope ? e->W("feat_rope.freqs_sin").d : nullptr;
+  if (k == "gemm_qkv") {
+    *work = 2.0 * M * 3.0 * D * D;
+    fn = [&] {
+      TcGemmArgs a = tc_args(e->A_h, D, e->lw[0].qkv, D, M, 3 * D, D, TC_EPI_QKV, e->W(blk(0, "attn.qkv.bias")).d);
+      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.qk_rms = c.use_rmsnorm; a.H = H;
+      a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
+      if (c.use_qknorm) { a.qn_w = e->W(blk(0, "attn.q_norm.weight")).d; a.kn_w = e->W(blk(0, "attn.k_norm.weight")).d; }
+      launch_gemm_tc(a, s);
+    };
+  } else if (k == "gemm_proj") {
+    *work = 2.0 * M * (double)D * D;
+    fn = [&] {
+      TcGemmArgs pr = tc_args(e->O_h, D, e->lw[0].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(0, "attn.proj.bias")).d);
+      pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NM; pr.gate_off = mo.gate_msa; pr.T = T;
+      launch_gemm_tc(pr, s);
+    };
+  } else if (k == "gemm_w12") {
+    VV_CHECK(c.use_swiglu, "gemm_w12 needs use_swiglu");
+    *work = 2.0 * M * 2.0 * S * D;
+    fn = [&] {
+      TcGemmArgs a = tc_args(e->A_h, D, e->lw[0].w1, D, M, 2 * S, D, TC_EPI_SWIGLU, e->lw[0].b1);
+      a.out = e->Hh_h; a.ldo = e->Spad;
+      launch_gemm_tc(a, s);
+    };
+  } else if (k == "gemm_w3") {
+    *work = 2.0 * M * (double)S * D;
+    fn = [&] {
+      TcGemmArgs a = tc_args(e->Hh_h, e->Spad, e->lw[0].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL,
+                             e->W(blk(0, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d);
+      a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NM; a.gate_off = mo.gate_mlp; a.T = T;
+      launch_gemm_tc(a, s);
+    };
+  } else if (k == "attention") {
+    *work = 4.0 * rows * (double)H * T * T * hd;
+    fn = [&] {
+      TcAttnArgs at;
+      at.q = e->q_h; at.k = e->k_h; at.vt = e->vt_h; at.out = e->O_h; at.B = rows; at.H = H; at.T = T; at.hd = hd;
+      at.hdp = e->hdp; at.hdv = e->hdv;
+      launch_attention_tc(at, s);
+    };
+  } else if (k == "norm_modulate") {
+    *work = (double)M * D * (4.0 + 2.0);  // bytes: read fp32 residual, write bf16 operand
+    fn = [&] { norm_mod(e, c.use_rmsnorm ? e->W(blk(0, "norm1.weight")).d : nullptr, mo.shift_msa, mo.scale_msa, M, s); };
+  } else if (k == "ode_update") {
+    ensure_state(e, rows);
+    const double el = (double)rows * e->C * e->img * e->img;
+    *work = el * 4.0 * 3.0;  // bytes: read v, read x, write x
+    VV_CUDA(cudaMemsetAsync(e->st, 0, 16, s));
+    fn = [&] {
+      OdeArgs o;
+      o.v = e->sv; o.x = e->sx; o.xp = e->sxp; o.k1 = e->sk1; o.trace = nullptr; o.t = e->st; o.rows = rows; o.C = e->C;
+      o.HW = e->img * e->img; o.use_cfg = rows % 2 == 0; o.scale = 1.0f; o.interval = 0; o.start = 0.f; o.channels = 3;
+      o.dt = 0.f; o.stage = 0;
+      launch_ode_update(o, s);
+    };
+  } else {
+    throw Error("time_kernel: unknown kernel '" + k + "'");
+  }
+  cudaEvent_t e0, e1;
+  VV_CUDA(cudaEventCreate(&e0));
+  VV_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) fn();
+  VV_CUDA(cudaEventRecord(e0, s));
+  for (int i = 0; i < iters; ++i) fn();
+  VV_CUDA(cudaEventRecord(e1, s));
+  VV_CUDA(cudaEventSynchronize(e1));
+  float total = 0.f;
+  VV_CUDA(cudaEventElapsedTime(&total, e0, e1));
+  *ms = total / (float)iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  VV_API_END()
+}
+
+}  // extern "C"

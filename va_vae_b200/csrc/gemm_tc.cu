@@ -1,0 +1,461 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:
+//   C[M,N] = A[M,K] (bf16, K-major) * W[N,K]^T (bf16, K-major), fp32 accumulation in TMEM.
+//   warp 0      : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
+//   warps 2..5  : epilogue - tcgen05.ld from TMEM (lane quarter = warp%4), fused epilogue, coalesced stores
+// Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1; shared-memory operand tiles run through an N-stage full/empty mbarrier ring.
+#include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
+
+#include <mutex>
+
+namespace vv {
+
+// ------------------------------------------------------------------------------------------------ host tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+      throw Error("cuTensorMapEncodeTiled entry point not available (driver too old?)");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+CUtensorMap make_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
+                              uint32_t box_inner, uint32_t box_outer) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  VV_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_pitch_bytes % 16 == 0, "tensor map alignment");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(2d) failed with code " + std::to_string((int)r));
+  return m;
+}
+CUtensorMap make_tmap_3d_bf16(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
+                              uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  VV_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && pitch1_bytes % 16 == 0 && pitch2_bytes % 16 == 0,
+           "tensor map alignment");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(3d) failed with code " + std::to_string((int)r));
+  return m;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+
+__device__ __forceinline__ float silu_fast(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// Per-row statistics over one head's hd accumulator columns (re-read from TMEM, 8 columns at a time).
+// Called with the warp converged (head boundaries depend on the column only).
+__device__ __noinline__ void qk_head_stats(uint32_t tbase, int hc0, int n0, int hd, const float* __restrict__ bias,
+                                           int rms, float& mean, float& rstd) {
+  float s1 = 0.f, s2 = 0.f;
+  for (int dd = 0; dd < hd; dd += 8) {
+    uint32_t t8[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(t8[0]), "=r"(t8[1]), "=r"(t8[2]), "=r"(t8[3]), "=r"(t8[4]), "=r"(t8[5]), "=r"(t8[6]),
+                   "=r"(t8[7])
+                 : "r"(tbase + hc0 + dd));
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float x = __uint_as_float(t8[e]) + bias[n0 + hc0 + dd + e];
+      s1 += x;
+      s2 += x * x;
+    }
+  }
+  if (rms) {
+    mean = 0.f;
+    rstd = rsqrtf(s2 / (float)hd + 1e-6f);
+  } else {
+    mean = s1 / (float)hd;
+    rstd = rsqrtf(fmaxf(s2 / (float)hd - mean * mean, 0.f) + 1e-5f);
+  }
+}
+
+struct TcSmemBars {
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+
+template <int EPI, int CW>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
+          const int BN, const int nstages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = TC_A_BYTES + BN * 128;
+  float* staging = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
+  TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(reinterpret_cast<uint8_t*>(staging) + 4 * 32 * (CW + 4) * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (a.M + TC_BM - 1) / TC_BM;
+  const int n_tiles = (a.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (a.K + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int i = 0; i < nstages; ++i) {
+      ptx::mbar_init(&bars->full[i], 1);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->tfull[i], 1);
+      ptx::mbar_init(&bars->tempty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + TC_A_BYTES;
+          ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+          ptx::tma_load_2d(sa, &tmA, &bars->full[stage], kb * TC_BK, m_blk * TC_BM);
+          ptx::tma_load_2d(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(TC_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&bars->tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * 256;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(&bars->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = ptx::make_desc_k_sw128(sa);
+          const uint64_t bdesc = ptx::make_desc_k_sw128(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+            ptx::umma_bf16_ss(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                              (uint32_t)((kb | k) != 0));
+          }
+          ptx::umma_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&bars->tfull[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    float* st = staging + (size_t)q * 32 * (CW + 4);
+    constexpr int LPR = CW / 4;   // lanes per row in the row-wise pass
+    constexpr int RPP = 32 / LPR; // rows per pass
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m0 = m_blk * TC_BM, n0 = n_blk * BN;
+      ptx::mbar_wait(&bars->tfull[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
+      const int my_row = m0 + q * 32 + lane;  // thread == row domain
+
+      // qk-norm statistics are computed on demand per head (thread == row domain)
+      float qk_mean = 0.f, qk_rstd = 1.f;
+      int qk_head = -1;
+
+      for (int c0 = 0; c0 < BN; c0 += CW) {
+        if (n0 + c0 >= a.N) break;
+        uint32_t r[CW];
+        if (CW == 32) ptx::tmem_ld_x32(tbase + c0, r);
+        else ptx::tmem_ld_x16(tbase + c0, r);
+        ptx::tmem_ld_wait();
+
+        if (EPI == TC_EPI_FINAL) {
+          // unpatchify (lightningdit.py:376-389): token-major column (pa*p+pb)*Cout + c -> NCHW; lanes are
+          // consecutive tokens so for p == 1 every store instruction writes 128 contiguous bytes.
+          if (my_row < a.M) {
+            const int rr = my_row / a.T, tok = my_row % a.T;
+            const int seg = rr / a.rm.seg_rows, ii = rr - seg * a.rm.seg_rows;
+            const int gw = a.img / a.p, ti = tok / gw, tj = tok % gw;
+            float* ob = reinterpret_cast<float*>(a.out) + (size_t)(a.rm.out_off[seg] + ii) * a.Ckeep * a.img * a.img;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              const int col = n0 + c0 + j;
+              if (col < a.N) {
+                const int c = col % a.Cout, ab = col / a.Cout, pa = ab / a.p, pb = ab % a.p;
+                if (c < a.Ckeep)
+                  ob[((size_t)c * a.img + ti * a.p + pa) * a.img + tj * a.p + pb] = __uint_as_float(r[j]) + a.bias[col];
+              }
+            }
+          }
+          continue;
+        }
+
+        if (EPI == TC_EPI_QKV) {
+          const int colc = n0 + c0;
+          const int D = a.H * a.hd;
+          const int which = colc / D;
+          if (which == 2) {
+            // V: store transposed (B,H,hdv,T): lanes = consecutive tokens -> 64 contiguous bytes per store
+            if (my_row < a.M) {
+              const int b = my_row / a.T, t = my_row % a.T;
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const int col = colc + j;
+                if (col < a.N) {
+                  const int rem = col - 2 * D, h = rem / a.hd, d = rem % a.hd;
+                  a.vt[(((size_t)b * a.H + h) * a.hdv + d) * a.T + t] =
+                      __float2bfloat16_rn(__uint_as_float(r[j]) + a.bias[col]);
+                }
+              }
+            }
+            continue;
+          }
+          // q / k: bias (+ optional qk-norm) in the thread == row domain, RoPE + store in the row-wise pass
+          const float* nw = which == 0 ? a.qn_w : a.kn_w;
+          const float* nb = which == 0 ? a.qn_b : a.kn_b;
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int col = colc + j;
+            float v = __uint_as_float(r[j]) + (col < a.N ? a.bias[col] : 0.f);
+            if (nw) {
+              const int rem = col - which * D, h = rem / a.hd, d = rem % a.hd;
+              if (h != qk_head) {
+                qk_head = h;
+                qk_head_stats(tbase, which * D + h * a.hd - n0, n0, a.hd, a.bias, a.qk_rms, qk_mean, qk_rstd);
+              }
+              v = (v - qk_mean) * qk_rstd * nw[d] + (nb ? nb[d] : 0.f);
+            }
+            r[j] = __float_as_uint(v);
+          }
+        }
+
+        // ---- stage the 32 x CW fp32 block in shared memory, then store row-wise (coalesced)
+        __syncwarp();
+#pragma unroll
+        for (int j4 = 0; j4 < CW / 4; ++j4)
+          *reinterpret_cast<float4*>(st + lane * (CW + 4) + j4 * 4) =
+              make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]), __uint_as_float(r[j4 * 4 + 2]),
+                          __uint_as_float(r[j4 * 4 + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int ps = 0; ps < LPR; ++ps) {
+          const int rr = ps * RPP + lane / LPR;
+          const int cc = (lane % LPR) * 4;
+          const int row = m0 + q * 32 + rr;
+          const int col = n0 + c0 + cc;
+          if (row >= a.M || col >= a.N) continue;
+          float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + cc);
+          if (EPI != TC_EPI_QKV && a.bias) {
+            float4 bb = *reinterpret_cast<const float4*>(a.bias + col);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+          }
+          if (EPI == TC_EPI_BIAS_F32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = v;
+          } else if (EPI == TC_EPI_BIAS_BF16 || EPI == TC_EPI_GELU_BF16) {
+            if (EPI == TC_EPI_GELU_BF16) {
+              v.x = gelu_tanh_fast(v.x); v.y = gelu_tanh_fast(v.y); v.z = gelu_tanh_fast(v.z); v.w = gelu_tanh_fast(v.w);
+            }
+            uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo + col) = pk;
+          } else if (EPI == TC_EPI_GATED_RESIDUAL) {
+            // x = x + gate.unsqueeze(1) * f(...)   lightningdit.py:248-249
+            const int b = row / a.T;
+            float4 g = *reinterpret_cast<const float4*>(a.mod + (size_t)b * a.mod_ld + a.gate_off + col);
+            float4* xp = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col);
+            float4 x = *xp;
+            x.x = fmaf(g.x, v.x, x.x); x.y = fmaf(g.y, v.y, x.y); x.z = fmaf(g.z, v.z, x.z); x.w = fmaf(g.w, v.w, x.w);
+            *xp = x;
+          } else if (EPI == TC_EPI_SWIGLU) {
+            // rows of w12 are interleaved at pack time: column 2j = x1[j] (gated), 2j+1 = x2[j]; swiglu_ffn.py:33-35
+            uint32_t pk = pack_bf16(silu_fast(v.x) * v.y, silu_fast(v.z) * v.w);
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo + (col >> 1)) = pk;
+          } else if (EPI == TC_EPI_QKV) {
+            const int D = a.H * a.hd;
+            const int which = col / D, rem = col - which * D, h = rem / a.hd, d = rem % a.hd;
+            const int b = row / a.T, t = row % a.T;
+            if (a.cos) {
+              // t*cos + rotate_half(t)*sin with (a,b) -> (-b,a) on adjacent pairs; pos_embed.py:38-42,135
+              float4 c4 = *reinterpret_cast<const float4*>(a.cos + (size_t)t * a.hd + d);
+              float4 s4 = *reinterpret_cast<const float4*>(a.sin + (size_t)t * a.hd + d);
+              float4 o;
+              o.x = v.x * c4.x - v.y * s4.x;
+              o.y = v.y * c4.y + v.x * s4.y;
+              o.z = v.z * c4.z - v.w * s4.z;
+              o.w = v.w * c4.w + v.z * s4.w;
+              v = o;
+            }
+            bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)b * a.H + h) * a.T + t) * a.hdp + d;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+          }
+        }
+      }
+      // release this accumulator stage to the MMA warp
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars->tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host launch
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev;
+    VV_CUDA(cudaGetDevice(&dev));
+    VV_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return g_num_sms;
+}
+
+int gemm_tc_pick_bn(const TcGemmArgs& a) {
+  if (a.epi == TC_EPI_FINAL) {
+    int bn = ((a.N + 15) / 16) * 16;
+    VV_CHECK(bn <= 256, "final linear wider than 256 columns is not supported");
+    return bn;
+  }
+  if (a.epi == TC_EPI_QKV && a.qn_w) {
+    // whole heads per tile so the per-head statistics live in one accumulator tile
+    int best = 0;
+    for (int bn = 16; bn <= 256; bn += 16)
+      if (bn % a.hd == 0 && (a.H * a.hd) % bn == 0) best = bn;
+    VV_CHECK(best > 0, "qk-norm epilogue: no tile width <= 256 holds whole heads (head_dim must divide a multiple of 16)");
+    return best;
+  }
+  const int cands[3] = {256, 192, 128};
+  int best = 128;
+  double best_eff = -1.0;
+  for (int i = 0; i < 3; ++i) {
+    int bn = cands[i];
+    if (a.epi == TC_EPI_QKV && (a.H * a.hd) % 16 != 0) continue;
+    double eff = (double)a.N / (double)(cdiv(a.N, bn) * bn);
+    // wave quantisation over the persistent grid
+    long tiles = (long)cdiv(a.M, TC_BM) * cdiv(a.N, bn);
+    long waves = (tiles + num_sms() - 1) / num_sms();
+    eff *= (double)tiles / (double)(waves * num_sms());
+    // wider tiles read less shared memory per flop (B200: 128 B/clk/SM smem vs 8192 flop/clk/SM tensor)
+    eff *= (bn >= 192 ? 1.0 : 0.93);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = bn; }
+  }
+  if (a.N <= 128) best = ((a.N + 15) / 16) * 16;
+  return best;
+}
+
+template <int EPI, int CW>
+static void launch_inst(const TcGemmArgs& a, int BN, cudaStream_t s) {
+  const int stage_bytes = TC_A_BYTES + BN * 128;
+  const int fixed = 4 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024;
+  int nstages = (227 * 1024 - fixed) / stage_bytes;
+  if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
+  VV_CHECK(nstages >= 2, "gemm_tc: tile too large for shared memory");
+  const size_t smem = (size_t)nstages * stage_bytes + fixed;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VV_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  CUtensorMap tmA = make_tmap_2d_bf16(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, TC_BK, TC_BM);
+  CUtensorMap tmB = make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK, (uint32_t)BN);
+  const int tiles = cdiv(a.M, TC_BM) * cdiv(a.N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  k_gemm_tc<EPI, CW><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a, BN, nstages);
+  VV_LAUNCH_CHECK();
+}
+
+template <int EPI>
+static void launch_epi(const TcGemmArgs& a, int BN, int cw, cudaStream_t s) {
+  if (cw == 32) launch_inst<EPI, 32>(a, BN, s);
+  else launch_inst<EPI, 16>(a, BN, s);
+}
+
+void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
+  VV_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tc: empty problem");
+  VV_CHECK(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm_tc: row pitch must be a multiple of 8 bf16 (16 bytes)");
+  const int BN = gemm_tc_pick_bn(a);
+  int cw = (BN % 32 == 0) ? 32 : 16;
+  if (a.epi == TC_EPI_QKV && (a.H * a.hd) % 32 != 0) cw = 16;
+  VV_CHECK(BN % cw == 0, "gemm_tc: tile width / chunk width mismatch");
+  if (a.epi != TC_EPI_FINAL) VV_CHECK(a.N % 4 == 0, "gemm_tc: N must be a multiple of 4");
+  switch (a.epi) {
+    case TC_EPI_BIAS_F32: launch_epi<TC_EPI_BIAS_F32>(a, BN, cw, s); break;
+    case TC_EPI_BIAS_BF16: launch_epi<TC_EPI_BIAS_BF16>(a, BN, cw, s); break;
+    case TC_EPI_GATED_RESIDUAL: launch_epi<TC_EPI_GATED_RESIDUAL>(a, BN, cw, s); break;
+    case TC_EPI_SWIGLU: launch_epi<TC_EPI_SWIGLU>(a, BN, cw, s); break;
+    case TC_EPI_GELU_BF16: launch_epi<TC_EPI_GELU_BF16>(a, BN, cw, s); break;
+    case TC_EPI_QKV:
+      VV_CHECK(a.hd % 8 == 0 && (a.H * a.hd) % 16 == 0, "qkv epilogue: head_dim % 8 and hidden % 16 required");
+      launch_epi<TC_EPI_QKV>(a, BN, cw, s);
+      break;
+    case TC_EPI_FINAL: launch_epi<TC_EPI_FINAL>(a, BN, cw, s); break;
+    default: throw Error("gemm_tc: unknown epilogue");
+  }
+}
+
+}  // namespace vv

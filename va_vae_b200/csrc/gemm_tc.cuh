@@ -1,0 +1,52 @@
+// tcgen05 / TMEM / TMA GEMM with fused epilogues (bf16 path).
+#pragma once
+#include "common.cuh"
+
+namespace vv {
+
+enum TcEpi {
+  TC_EPI_BIAS_F32 = 0,       // out f32 [M, ldo] = acc + bias                       (adaLN, tests)
+  TC_EPI_BIAS_BF16 = 1,      // out bf16 = acc + bias
+  TC_EPI_GATED_RESIDUAL = 2, // X f32 [M, ldo] += gate[b] * (acc + bias)            (attn.proj, mlp.w3 / fc2)
+  TC_EPI_SWIGLU = 3,         // out bf16 [M, ldo][n/2] = silu(v[2j]) * v[2j+1]      (mlp.w12, rows interleaved)
+  TC_EPI_GELU_BF16 = 4,      // out bf16 = gelu_tanh(acc + bias)                    (legacy mlp.fc1)
+  TC_EPI_QKV = 5,            // bias, [qk-norm], RoPE, scatter q,k (B,H,T,hdp) / v^T (B,H,hdv,T)
+  TC_EPI_FINAL = 6,          // acc + bias -> unpatchify -> NCHW rows of the caller  (final_layer.linear)
+};
+
+struct TcGemmArgs {
+  const bf16* A;   // [M, K] row-major, row pitch lda elements (lda % 8 == 0)
+  int lda;
+  const bf16* W;   // [N, K] row-major (nn.Linear layout), row pitch ldw elements
+  int ldw;
+  int M, N, K;
+  int epi;
+  const float* bias;  // [N] (already interleaved for SWIGLU) or null
+  void* out;          // see TcEpi
+  int ldo;
+  // gated residual
+  const float* mod;   // [rows, mod_ld]
+  int mod_ld, gate_off, T;
+  // qkv
+  bf16 *q, *k, *vt;
+  const float *cos, *sin;  // [T, hd] or null
+  const float *qn_w, *qn_b, *kn_w, *kn_b;
+  int qk_rms;
+  int H, hd, hdp, hdv;
+  // final
+  int p, Cout, Ckeep, img;
+  RowMap rm;
+};
+
+void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
+int gemm_tc_pick_bn(const TcGemmArgs& a);
+
+struct TcAttnArgs {
+  const bf16 *q, *k;  // (B,H,T,hdp)
+  const bf16* vt;     // (B,H,hdv,T)
+  bf16* out;          // [B*T, H*hd]
+  int B, H, T, hd, hdp, hdv;
+};
+void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s);
+
+}  // namespace vv

@@ -1,0 +1,482 @@
+// Bandwidth-bound kernels of the LightningDiT forward + the fused CFG/ODE update.
+// All are single-pass, vectorised and coalesced; reductions use warp shuffles.
+// Math follows SURVEY.md Appendix A (reference: LightningDiT/models/lightningdit.py).
+#include "common.cuh"
+
+namespace vv {
+
+thread_local LaunchCounter* g_counter = nullptr;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ int rm_seg(const RowMap& rm, int r, int& i) {
+  int s = r / rm.seg_rows;
+  i = r - s * rm.seg_rows;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patch embed (conv k=s=p as a per-token GEMV) + bias + pos_embed -> fp32 residual stream.
+// lightningdit.py:402.  grid = (ceil(T/16), rows), block = 256; thread owns output columns d.
+// ------------------------------------------------------------------------------------------------
+constexpr int EMB_TOK = 16;
+__global__ void __launch_bounds__(256) k_patch_embed(EmbedArgs a) {
+  extern __shared__ float xin[];  // [Cpp][EMB_TOK]
+  const int row = blockIdx.y;
+  const int tok0 = blockIdx.x * EMB_TOK;
+  const int p = a.p, pp = p * p, Cpp = a.C * pp;
+  const int gw = a.img / p;  // tokens per image row
+  int i;
+  int seg = rm_seg(a.rm, row, i);
+  const float* xr = a.x + (size_t)(a.rm.x_off[seg] + i) * a.C * a.img * a.img;
+  for (int e = threadIdx.x; e < Cpp * EMB_TOK; e += blockDim.x) {
+    int k = e / EMB_TOK, j = e % EMB_TOK;
+    int tok = tok0 + j;
+    float val = 0.f;
+    if (tok < a.T) {
+      int c = k / pp, ab = k % pp, pa = ab / p, pb = ab % p;
+      int ti = tok / gw, tj = tok % gw;
+      val = xr[((size_t)c * a.img + ti * p + pa) * a.img + tj * p + pb];
+    }
+    xin[k * EMB_TOK + j] = val;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+    float acc[EMB_TOK];
+#pragma unroll
+    for (int j = 0; j < EMB_TOK; ++j) acc[j] = 0.f;
+    for (int k = 0; k < Cpp; ++k) {
+      float w = a.wT[(size_t)k * a.D + d];
+      const float4* xv = reinterpret_cast<const float4*>(xin + k * EMB_TOK);
+#pragma unroll
+      for (int j4 = 0; j4 < EMB_TOK / 4; ++j4) {
+        float4 x4 = xv[j4];
+        acc[j4 * 4 + 0] = fmaf(w, x4.x, acc[j4 * 4 + 0]);
+        acc[j4 * 4 + 1] = fmaf(w, x4.y, acc[j4 * 4 + 1]);
+        acc[j4 * 4 + 2] = fmaf(w, x4.z, acc[j4 * 4 + 2]);
+        acc[j4 * 4 + 3] = fmaf(w, x4.w, acc[j4 * 4 + 3]);
+      }
+    }
+    float b = a.bias[d];
+#pragma unroll
+    for (int j = 0; j < EMB_TOK; ++j) {
+      int tok = tok0 + j;
+      if (tok < a.T) a.X[((size_t)row * a.T + tok) * a.D + d] = acc[j] + b + a.pos[(size_t)tok * a.D + d];
+    }
+  }
+}
+void launch_patch_embed(const EmbedArgs& a, cudaStream_t s) {
+  dim3 grid(cdiv(a.T, EMB_TOK), a.rows);
+  size_t smem = (size_t)a.C * a.p * a.p * EMB_TOK * sizeof(float);
+  k_patch_embed<<<grid, 256, smem, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sinusoidal timestep features [cos | sin], lightningdit.py:121-126 (freqs uploaded from the host so
+// they are bit-identical to the reference's torch.exp).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_tfreq(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out,
+                        int rows, RowMap rm) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 128) return;
+  int r = idx >> 7, k = idx & 127;
+  int i;
+  int seg = rm_seg(rm, r, i);
+  float tv = t[(size_t)(rm.t_off[seg] + i) * rm.t_stride];
+  float arg = tv * freqs[k];
+  out[(size_t)r * 256 + k] = cosf(arg);
+  out[(size_t)r * 256 + 128 + k] = sinf(arg);
+}
+void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowMap rm, cudaStream_t s) {
+  k_tfreq<<<cdiv(rows * 128, 256), 256, 0, s>>>(t, freqs, out, rows, rm);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm / LayerNorm + adaLN modulate, one warp per token row, row kept in registers.
+// rmsnorm.py:63,76-77 ; lightningdit.py:26-30.   out = norm(x)*w*(1+scale)+shift
+// ------------------------------------------------------------------------------------------------
+constexpr int NM_MAXV = 16;  // float4 per lane -> D <= 2048
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) k_norm_modulate(NormModArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.M) return;
+  const int row = warp;
+  const int b = row / a.T;
+  const float4* xr = reinterpret_cast<const float4*>(a.X + (size_t)row * a.D);
+  const int nv = a.D >> 2;
+  float4 v[NM_MAXV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NM_MAXV; ++i) {
+    int c = i * 32 + lane;
+    if (c < nv) {
+      v[i] = xr[c];
+      s1 += v[i].x + v[i].y + v[i].z + v[i].w;
+      s2 += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+  s2 = warp_sum(s2);
+  float mean = 0.f, rstd;
+  const float invD = 1.0f / (float)a.D;
+  if (a.w) {
+    rstd = rsqrtf(s2 * invD + 1e-6f);
+  } else {
+    s1 = warp_sum(s1);
+    mean = s1 * invD;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < NM_MAXV; ++i) {
+      int c = i * 32 + lane;
+      if (c < nv) {
+        float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        var += dx * dx + dy * dy + dz * dz + dw * dw;
+      }
+    }
+    var = warp_sum(var) * invD;
+    rstd = rsqrtf(var + 1e-6f);
+  }
+  const float* modr = a.mod + (size_t)b * a.mod_ld;
+  const float4* sc = reinterpret_cast<const float4*>(modr + a.scale_off);
+  const float4* sh = a.shift_off >= 0 ? reinterpret_cast<const float4*>(modr + a.shift_off) : nullptr;
+  const float4* w4 = a.w ? reinterpret_cast<const float4*>(a.w) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NM_MAXV; ++i) {
+    int c = i * 32 + lane;
+    if (c < nv) {
+      float4 x = v[i];
+      float4 g = sc[c];
+      float4 w = w4 ? w4[c] : make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 h = sh ? sh[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 o;
+      o.x = ((x.x - mean) * rstd) * w.x * (1.f + g.x) + h.x;
+      o.y = ((x.y - mean) * rstd) * w.y * (1.f + g.y) + h.y;
+      o.z = ((x.z - mean) * rstd) * w.z * (1.f + g.z) + h.z;
+      o.w = ((x.w - mean) * rstd) * w.w * (1.f + g.w) + h.w;
+      if (OUT_BF16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo)[c] = pk;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo)[c] = o;
+      }
+    }
+  }
+}
+void launch_norm_modulate(const NormModArgs& a, cudaStream_t s) {
+  VV_CHECK(a.D % 4 == 0 && a.D <= NM_MAXV * 128, "norm_modulate: hidden size must be a multiple of 4 and <= 2048");
+  VV_CHECK(a.mod_ld % 4 == 0 && a.scale_off % 4 == 0 && (a.shift_off < 0 || a.shift_off % 4 == 0) && a.ldo % 4 == 0,
+           "norm_modulate: alignment");
+  int grid = cdiv(a.M, 8);
+  if (a.out_bf16)
+    k_norm_modulate<true><<<grid, 256, 0, s>>>(a);
+  else
+    k_norm_modulate<false><<<grid, 256, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 validation path: split qkv, optional qk-norm, RoPE, scatter to (B,H,T,hd).
+// lightningdit.py:68-74 ; pos_embed.py:38-42,135.  One warp per (token row, head).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_qkv_post_f32(QkvPostArgs a) {
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = row / a.T, t = row % a.T;
+  const int D = a.H * a.hd, hd = a.hd;
+  for (int h = warp; h < a.H; h += 4) {
+    for (int which = 0; which < 3; ++which) {
+      const float* src = a.qkv + (size_t)row * 3 * D + (size_t)which * D + h * hd;
+      float* dst = (which == 0 ? a.q : which == 1 ? a.k : a.v) + (((size_t)b * a.H + h) * a.T + t) * hd;
+      const float* nw = which == 0 ? a.qn_w : a.kn_w;
+      const float* nb = which == 0 ? a.qn_b : a.kn_b;
+      // up to 4 pairs per lane (hd <= 256)
+      float pa[4], pb[4];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int pr = i * 32 + lane;
+        pa[i] = pb[i] = 0.f;
+        if (pr * 2 < hd) {
+          float2 xy = *reinterpret_cast<const float2*>(src + pr * 2);
+          pa[i] = xy.x;
+          pb[i] = xy.y;
+          s1 += xy.x + xy.y;
+          s2 += xy.x * xy.x + xy.y * xy.y;
+        }
+      }
+      if (which < 2 && nw) {
+        float mean = 0.f, rstd;
+        if (a.rms) {
+          rstd = rsqrtf(warp_sum(s2) / (float)hd + 1e-6f);
+        } else {
+          mean = warp_sum(s1) / (float)hd;
+          float var = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int pr = i * 32 + lane;
+            if (pr * 2 < hd) var += (pa[i] - mean) * (pa[i] - mean) + (pb[i] - mean) * (pb[i] - mean);
+          }
+          rstd = rsqrtf(warp_sum(var) / (float)hd + 1e-5f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int pr = i * 32 + lane;
+          if (pr * 2 < hd) {
+            pa[i] = (pa[i] - mean) * rstd * nw[pr * 2] + (nb ? nb[pr * 2] : 0.f);
+            pb[i] = (pb[i] - mean) * rstd * nw[pr * 2 + 1] + (nb ? nb[pr * 2 + 1] : 0.f);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int pr = i * 32 + lane;
+        if (pr * 2 < hd) {
+          float x = pa[i], y = pb[i];
+          if (which < 2 && a.cos) {
+            float c0 = a.cos[(size_t)t * hd + pr * 2], c1 = a.cos[(size_t)t * hd + pr * 2 + 1];
+            float s0 = a.sin[(size_t)t * hd + pr * 2], s1v = a.sin[(size_t)t * hd + pr * 2 + 1];
+            float nx = x * c0 - y * s0;  // t*cos + rotate_half(t)*sin, rotate_half: (a,b)->(-b,a)
+            float ny = y * c1 + x * s1v;
+            x = nx;
+            y = ny;
+          }
+          *reinterpret_cast<float2*>(dst + pr * 2) = make_float2(x, y);
+        }
+      }
+    }
+  }
+}
+void launch_qkv_post_f32(const QkvPostArgs& a, cudaStream_t s) {
+  VV_CHECK(a.hd % 2 == 0 && a.hd <= 256, "qkv_post: head_dim must be even and <= 256");
+  k_qkv_post_f32<<<a.M, 128, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 validation attention: softmax(q k^T / sqrt(hd)) v, one warp per query.
+// lightningdit.py:77-88.  out is token-major [B*T, H*hd].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_attention_f32(const float* __restrict__ q, const float* __restrict__ k,
+                                                      const float* __restrict__ v, float* __restrict__ out, int B,
+                                                      int H, int T, int hd) {
+  extern __shared__ float sm[];  // per warp: scores[T] + qrow[hd]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bh = blockIdx.y;
+  const int b = bh / H, h = bh % H;
+  const int qi = blockIdx.x * 4 + warp;
+  if (qi >= T) return;
+  float* sc = sm + (size_t)warp * (T + hd);
+  float* qs = sc + T;
+  const float* qr = q + ((size_t)bh * T + qi) * hd;
+  const float* kb = k + (size_t)bh * T * hd;
+  const float* vb = v + (size_t)bh * T * hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  for (int d = lane; d < hd; d += 32) qs[d] = qr[d] * scale;
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < T; j += 32) {
+    const float* kr = kb + (size_t)j * hd;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc = fmaf(qs[d], kr[d], acc);
+    sc[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  for (int d = lane; d < hd; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc = fmaf(sc[j], vb[(size_t)j * hd + d], acc);
+    out[((size_t)b * T + qi) * (H * hd) + h * hd + d] = acc * inv;
+  }
+}
+void launch_attention_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int T, int hd,
+                          cudaStream_t s) {
+  dim3 grid(cdiv(T, 4), B * H);
+  size_t smem = (size_t)4 * (T + hd) * sizeof(float);
+  k_attention_f32<<<grid, 128, smem, s>>>(q, k, v, out, B, H, T, hd);
+  VV_LAUNCH_CHECK();
+}
+
+// X += gate[b] * Y   (lightningdit.py:248-249), fp32 validation path
+__global__ void k_gated_residual_f32(float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ mod,
+                                     int mod_ld, int gate_off, size_t total4, int D4, int T) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  size_t row = idx / D4;
+  int c4 = (int)(idx % D4);
+  int b = (int)(row / T);
+  float4 g = reinterpret_cast<const float4*>(mod + (size_t)b * mod_ld + gate_off)[c4];
+  float4 x = reinterpret_cast<float4*>(X)[idx];
+  float4 y = reinterpret_cast<const float4*>(Y)[idx];
+  x.x += g.x * y.x;
+  x.y += g.y * y.y;
+  x.z += g.z * y.z;
+  x.w += g.w * y.w;
+  reinterpret_cast<float4*>(X)[idx] = x;
+}
+void launch_gated_residual_f32(float* X, const float* Y, const float* mod, int mod_ld, int gate_off, int M, int D,
+                               int T, cudaStream_t s) {
+  size_t total4 = (size_t)M * (D / 4);
+  k_gated_residual_f32<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(X, Y, mod, mod_ld, gate_off, total4, D / 4, T);
+  VV_LAUNCH_CHECK();
+}
+
+// Hh = silu(U[:, :S]) * U[:, S:]   (swiglu_ffn.py:33-35), fp32 validation path
+__global__ void k_swiglu_f32(const float* __restrict__ U, float* __restrict__ Hh, size_t total, int S, int ldu,
+                             int ldh) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  size_t row = idx / S;
+  int j = (int)(idx % S);
+  float x1 = U[row * ldu + j], x2 = U[row * ldu + S + j];
+  Hh[row * ldh + j] = (x1 / (1.0f + expf(-x1))) * x2;
+}
+void launch_swiglu_f32(const float* U, float* Hh, int M, int S, int ldu, int ldh, cudaStream_t s) {
+  size_t total = (size_t)M * S;
+  k_swiglu_f32<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(U, Hh, total, S, ldu, ldh);
+  VV_LAUNCH_CHECK();
+}
+
+// unpatchify (lightningdit.py:376-389) + learn_sigma chunk (:416-417): token-major -> NCHW rows of the caller
+__global__ void k_unpatchify(UnpatchArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t per_row = (size_t)a.Ckeep * a.img * a.img;
+  if (idx >= per_row * a.rows) return;
+  int r = (int)(idx / per_row);
+  int rem = (int)(idx % per_row);
+  int c = rem / (a.img * a.img);
+  int yx = rem % (a.img * a.img);
+  int yy = yx / a.img, xx = yx % a.img;
+  int gw = a.img / a.p;
+  int ti = yy / a.p, pa = yy % a.p, tj = xx / a.p, pb = xx % a.p;
+  int tok = ti * gw + tj;
+  int col = (pa * a.p + pb) * a.Cout + c;
+  int i;
+  int seg = rm_seg(a.rm, r, i);
+  a.out[(size_t)(a.rm.out_off[seg] + i) * per_row + rem] = a.Y[((size_t)r * a.T + tok) * (a.p * a.p * a.Cout) + col];
+}
+void launch_unpatchify(const UnpatchArgs& a, cudaStream_t s) {
+  size_t total = (size_t)a.rows * a.Ckeep * a.img * a.img;
+  k_unpatchify<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// CFG combine for the forward_with_cfg API (lightningdit.py:428-442): guidance on the first
+// `channels` channels; both halves receive the guided value; remaining channels pass through.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lerp_cfg(float4 c, float4 u, float s) {
+  return make_float4(u.x + s * (c.x - u.x), u.y + s * (c.y - u.y), u.z + s * (c.z - u.z), u.w + s * (c.w - u.w));
+}
+__global__ void k_cfg_combine(CfgArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index within the first half
+  const int HW4 = a.HW >> 2;
+  size_t half4 = (size_t)a.n * a.C * HW4;
+  if (idx >= half4) return;
+  int c = (int)((idx / HW4) % a.C);
+  const bool guided = !(a.interval && (a.t[0] < a.start));
+  float4 vc = reinterpret_cast<const float4*>(a.v)[idx];
+  float4 vu = reinterpret_cast<const float4*>(a.v)[idx + half4];
+  if (c < a.channels) {
+    float4 g = guided ? lerp_cfg(vc, vu, a.scale) : vc;
+    vc = g;
+    vu = g;
+  }
+  reinterpret_cast<float4*>(a.out)[idx] = vc;
+  reinterpret_cast<float4*>(a.out)[idx + half4] = vu;
+}
+void launch_cfg_combine(const CfgArgs& a, cudaStream_t s) {
+  VV_CHECK(a.HW % 4 == 0, "cfg_combine: H*W must be a multiple of 4");
+  size_t half4 = (size_t)a.n * a.C * (a.HW / 4);
+  k_cfg_combine<<<(unsigned)((half4 + 255) / 256), 256, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused CFG-combine + fixed-grid ODE update (Euler / Heun stages), one pass over the latents.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 axpy4(float4 x, float a, float4 v) {
+  return make_float4(x.x + a * v.x, x.y + a * v.y, x.z + a * v.z, x.w + a * v.w);
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__device__ __forceinline__ void ode_apply(const OdeArgs& a, size_t i4, float4 vh) {
+  float4* x4 = reinterpret_cast<float4*>(a.x);
+  if (a.trace) reinterpret_cast<float4*>(a.trace)[i4] = vh;
+  if (a.stage == 0) {
+    x4[i4] = axpy4(x4[i4], a.dt, vh);
+  } else if (a.stage == 1) {
+    reinterpret_cast<float4*>(a.k1)[i4] = vh;
+    reinterpret_cast<float4*>(a.xp)[i4] = axpy4(x4[i4], a.dt, vh);
+  } else {
+    float4 k1 = reinterpret_cast<const float4*>(a.k1)[i4];
+    x4[i4] = axpy4(x4[i4], a.dt * 0.5f, add4(k1, vh));
+  }
+}
+__global__ void k_ode_update(OdeArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW4 = a.HW >> 2;
+  if (a.use_cfg) {
+    const int n = a.rows >> 1;
+    size_t half4 = (size_t)n * a.C * HW4;
+    if (idx >= half4) return;
+    int c = (int)((idx / HW4) % a.C);
+    const bool guided = !(a.interval && (a.t[0] < a.start));
+    float4 vc = reinterpret_cast<const float4*>(a.v)[idx];
+    float4 vu = reinterpret_cast<const float4*>(a.v)[idx + half4];
+    if (c < a.channels) {
+      float4 g = guided ? lerp_cfg(vc, vu, a.scale) : vc;
+      vc = g;
+      vu = g;
+    }
+    ode_apply(a, idx, vc);
+    ode_apply(a, idx + half4, vu);
+  } else {
+    size_t tot4 = (size_t)a.rows * a.C * HW4;
+    if (idx >= tot4) return;
+    ode_apply(a, idx, reinterpret_cast<const float4*>(a.v)[idx]);
+  }
+}
+void launch_ode_update(const OdeArgs& a, cudaStream_t s) {
+  VV_CHECK(a.HW % 4 == 0, "ode_update: H*W must be a multiple of 4");
+  size_t work4 = (size_t)(a.use_cfg ? a.rows / 2 : a.rows) * a.C * (a.HW / 4);
+  k_ode_update<<<(unsigned)((work4 + 255) / 256), 256, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+__global__ void k_f32_to_bf16(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+void launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid == 0) return;
+  k_f32_to_bf16<<<grid, 256, 0, s>>>(in, out, n);
+  VV_LAUNCH_CHECK();
+}
+
+}  // namespace vv

@@ -1,0 +1,253 @@
+"""ctypes binding of libvavae_b200.so (C ABI: include/vavae_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or no sm_100 device is present,
+every entry point raises.  PyTorch is used only for device memory, streams and
+torch.distributed plumbing; all arithmetic happens in the library's own CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvavae_b200.so")
+
+PREC_BF16, PREC_FP32 = 0, 1
+ODE_EULER, ODE_HEUN = 0, 1
+ABI_VERSION = 1
+
+EXPORTS = [
+    "vavae_abi_version", "vavae_last_error", "vavae_create", "vavae_destroy", "vavae_load_weight", "vavae_finalize",
+    "vavae_forward", "vavae_forward_with_cfg", "vavae_sample_ode", "vavae_sample_ode_host", "vavae_launch_count",
+    "vavae_device_bytes", "vavae_test_gemm_bf16", "vavae_test_attention_bf16", "vavae_time_kernel",
+    "vavae_set_attention_variant",
+]
+
+
+class VavaeConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "abi_version", "input_size", "patch_size", "in_channels", "hidden_size", "depth", "num_heads", "mlp_hidden",
+        "num_classes", "label_rows", "learn_sigma", "use_qknorm", "use_swiglu", "use_rope", "use_rmsnorm", "wo_shift",
+        "precision", "max_chunk_rows")]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads the in-tree shared library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -m va_vae_b200.build` (nvcc, sm_100a). "
+            "This engine has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    c_void, c_int, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.vavae_abi_version.restype = c_int
+    lib.vavae_last_error.restype = ctypes.c_char_p
+    lib.vavae_create.argtypes = [ctypes.POINTER(VavaeConfig), c_int, ctypes.POINTER(c_void)]
+    lib.vavae_destroy.argtypes = [c_void]
+    lib.vavae_load_weight.argtypes = [c_void, ctypes.c_char_p, c_void, ctypes.POINTER(ctypes.c_int64), c_int, c_int]
+    lib.vavae_finalize.argtypes = [c_void, c_void]
+    lib.vavae_forward.argtypes = [c_void, c_void, c_void, c_void, c_void, c_int, c_void]
+    lib.vavae_forward_with_cfg.argtypes = [c_void, c_void, c_void, c_void, c_float, c_int, c_float, c_int, c_void, c_int,
+                                           c_void]
+    lib.vavae_sample_ode.argtypes = [c_void, c_void, c_void, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float,
+                                     c_int, c_float, c_int, c_void, c_void, c_int, c_void]
+    lib.vavae_sample_ode_host.argtypes = [c_void, c_void, c_void, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float,
+                                          c_int, c_float, c_int, c_void, c_int, c_void]
+    lib.vavae_launch_count.argtypes = [c_void]
+    lib.vavae_launch_count.restype = ctypes.c_uint64
+    lib.vavae_device_bytes.argtypes = [c_void]
+    lib.vavae_device_bytes.restype = ctypes.c_uint64
+    lib.vavae_test_gemm_bf16.argtypes = [c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_void]
+    lib.vavae_test_attention_bf16.argtypes = [c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_void]
+    lib.vavae_time_kernel.argtypes = [c_void, ctypes.c_char_p, c_int, c_int, ctypes.POINTER(c_float),
+                                      ctypes.POINTER(ctypes.c_double), c_void]
+    lib.vavae_set_attention_variant.argtypes = [c_int]
+    if lib.vavae_abi_version() != ABI_VERSION:
+        raise RuntimeError("libvavae_b200.so ABI version mismatch; rebuild with python -m va_vae_b200.build --force")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError("vavae_b200: " + load_library().vavae_last_error().decode())
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class Engine:
+    """One engine per (process, GPU).  Mirrors the lifetime of a LightningDiT module on a device."""
+
+    def __init__(self, config: dict, state_dict: Dict[str, torch.Tensor], device, precision: str = "bf16",
+                 max_chunk_rows: int = 0):
+        lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("vavae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("vavae_b200 engines live on CUDA devices only")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self.precision = precision
+        cfg = VavaeConfig(abi_version=ABI_VERSION, precision={"bf16": PREC_BF16, "fp32": PREC_FP32}[precision],
+                          max_chunk_rows=int(max_chunk_rows), **{k: int(v) for k, v in config.items()})
+        self.config = dict(config)
+        self._h = ctypes.c_void_p()
+        _check(lib.vavae_create(ctypes.byref(cfg), dev_index, ctypes.byref(self._h)))
+        self._lib = lib
+        try:
+            with torch.cuda.device(self.device):
+                for name, tensor in state_dict.items():
+                    if not torch.is_floating_point(tensor):
+                        continue
+                    t = tensor.detach()
+                    on_dev = t.is_cuda and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous()
+                    t = t if on_dev else t.to(dtype=torch.float32).contiguous()
+                    shape = (ctypes.c_int64 * max(t.dim(), 1))(*(t.shape if t.dim() else (1,)))
+                    _check(lib.vavae_load_weight(self._h, name.encode(), ctypes.c_void_p(t.data_ptr()), shape,
+                                                 max(t.dim(), 1), 1 if t.is_cuda else 0))
+                _check(lib.vavae_finalize(self._h, ctypes.c_void_p(_stream(self.device))))
+        except Exception:
+            lib.vavae_destroy(self._h)
+            self._h = None
+            raise
+        self.C, self.img = int(config["in_channels"]), int(config["input_size"])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vavae_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- LightningDiT.forward (models/lightningdit.py:391-418)
+    def forward(self, x: torch.Tensor, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        x, t = _f32(x, self.device), _f32(t, self.device)
+        y = y.to(device=self.device, dtype=torch.int64).contiguous()
+        self._check_x(x)
+        if t.shape != (x.shape[0],) or y.shape != (x.shape[0],):
+            raise ValueError("t and y must have shape (N,)")
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _check(self._lib.vavae_forward(self._h, x.data_ptr(), t.data_ptr(), y.data_ptr(), out.data_ptr(),
+                                           x.shape[0], ctypes.c_void_p(_stream(self.device))))
+        return out
+
+    # -- LightningDiT.forward_with_cfg (models/lightningdit.py:420-442)
+    def forward_with_cfg(self, x, t, y, cfg_scale, cfg_interval=None, cfg_interval_start=None, cfg_channels=3):
+        x, t = _f32(x, self.device), _f32(t, self.device)
+        y = y.to(device=self.device, dtype=torch.int64).contiguous()
+        self._check_x(x)
+        if x.shape[0] % 2:
+            raise ValueError("forward_with_cfg expects 2n rows (conditional rows then null-label rows)")
+        interval = 1 if cfg_interval is True else 0
+        start = float(cfg_interval_start) if (interval and cfg_interval_start is not None) else 0.0
+        if interval and cfg_interval_start is None:
+            raise TypeError("'<' not supported between instances of 'Tensor' and 'NoneType'")  # reference behaviour
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _check(self._lib.vavae_forward_with_cfg(self._h, x.data_ptr(), t.data_ptr(), y.data_ptr(), float(cfg_scale),
+                                                    interval, start, int(cfg_channels), out.data_ptr(), x.shape[0],
+                                                    ctypes.c_void_p(_stream(self.device))))
+        return out
+
+    # -- ode.sample over a fixed grid (transport/integrators.py:107-126)
+    def sample_ode(self, z, y, t_grid, method="euler", use_cfg=True, cfg_scale=1.0, cfg_interval=None,
+                   cfg_interval_start=None, cfg_channels=3, return_trace=False):
+        z = _f32(z, self.device)
+        y = y.to(device=self.device, dtype=torch.int64).contiguous()
+        self._check_x(z)
+        grid = torch.as_tensor(t_grid, dtype=torch.float32).cpu().contiguous()
+        meth = {"euler": ODE_EULER, "heun": ODE_HEUN, "heun2": ODE_HEUN}[method]
+        n_evals = (len(grid) - 1) * (2 if meth == ODE_HEUN else 1)
+        out = torch.empty_like(z)
+        trace = torch.empty((n_evals,) + tuple(z.shape), device=self.device, dtype=torch.float32) if return_trace else None
+        interval = 1 if cfg_interval is True else 0
+        start = float(cfg_interval_start) if (interval and cfg_interval_start is not None) else 0.0
+        gptr = ctypes.cast(grid.data_ptr(), ctypes.POINTER(ctypes.c_float))
+        with torch.cuda.device(self.device):
+            _check(self._lib.vavae_sample_ode(
+                self._h, z.data_ptr(), y.data_ptr(), gptr, len(grid), meth, 1 if use_cfg else 0, float(cfg_scale),
+                interval, start, int(cfg_channels), out.data_ptr(), trace.data_ptr() if return_trace else None,
+                z.shape[0], ctypes.c_void_p(_stream(self.device))))
+        return (out, trace) if return_trace else out
+
+    def sample_ode_host(self, z_host, y_host, t_grid, out_host, method="euler", use_cfg=True, cfg_scale=1.0,
+                        cfg_interval=None, cfg_interval_start=None, cfg_channels=3):
+        """End-to-end entry: HOST (ideally pinned) buffers in and out; H2D/D2H inside the call."""
+        assert z_host.dtype == torch.float32 and not z_host.is_cuda and z_host.is_contiguous()
+        assert y_host.dtype == torch.int64 and not y_host.is_cuda and y_host.is_contiguous()
+        assert out_host.dtype == torch.float32 and not out_host.is_cuda and out_host.shape == z_host.shape
+        grid = torch.as_tensor(t_grid, dtype=torch.float32).cpu().contiguous()
+        meth = {"euler": ODE_EULER, "heun": ODE_HEUN, "heun2": ODE_HEUN}[method]
+        interval = 1 if cfg_interval is True else 0
+        start = float(cfg_interval_start) if (interval and cfg_interval_start is not None) else 0.0
+        gptr = ctypes.cast(grid.data_ptr(), ctypes.POINTER(ctypes.c_float))
+        with torch.cuda.device(self.device):
+            _check(self._lib.vavae_sample_ode_host(
+                self._h, z_host.data_ptr(), y_host.data_ptr(), gptr, len(grid), meth, 1 if use_cfg else 0,
+                float(cfg_scale), interval, start, int(cfg_channels), out_host.data_ptr(), z_host.shape[0],
+                ctypes.c_void_p(_stream(self.device))))
+        return out_host
+
+    def time_kernel(self, kernel: str, rows: int, iters: int = 10):
+        """(ms per launch, algorithmic work) of one production kernel on layer-0 weights; CUDA events on the
+        current stream."""
+        ms, work = ctypes.c_float(), ctypes.c_double()
+        with torch.cuda.device(self.device):
+            _check(self._lib.vavae_time_kernel(self._h, kernel.encode(), rows, iters, ctypes.byref(ms),
+                                               ctypes.byref(work), ctypes.c_void_p(_stream(self.device))))
+        return ms.value, work.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vavae_launch_count(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._lib.vavae_device_bytes(self._h))
+
+    def _check_x(self, x):
+        if x.dim() != 4 or x.shape[1] != self.C or x.shape[2] != self.img or x.shape[3] != self.img:
+            raise ValueError(f"expected x of shape (N, {self.C}, {self.img}, {self.img}), got {tuple(x.shape)}")
+
+
+def test_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    lib = load_library()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        _check(lib.vavae_test_gemm_bf16(A.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                        out.data_ptr(), M, N, K, ctypes.c_void_p(_stream(A.device))))
+    return out
+
+
+def test_attention_bf16(q, k, vt, hd: int, p_in_tmem: bool = True) -> torch.Tensor:
+    """q,k: (B,H,T,hdp) bf16; vt: (B,H,hdv,T) bf16 -> (B*T, H*hd) bf16."""
+    lib = load_library()
+    B, H, T, _ = q.shape
+    out = torch.empty(B * T, H * hd, device=q.device, dtype=torch.bfloat16)
+    lib.vavae_set_attention_variant(1 if p_in_tmem else 0)
+    with torch.cuda.device(q.device):
+        _check(lib.vavae_test_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, T, hd,
+                                             ctypes.c_void_p(_stream(q.device))))
+    return out

@@ -1,0 +1,214 @@
+"""Mirror of the reference's `transport` sampling API (create_transport / Sampler.sample_ode), ODE side only.
+
+Reference: /root/reference/LightningDiT/transport/__init__.py:3-72 (create_transport),
+transport/transport.py:40-111,218-250,270-283,398-443 (Transport.check_interval / get_drift, Sampler.sample_ode),
+transport/integrators.py:77-126 (class ode).  Training losses, SDE sampling and likelihoods are out of
+scope for this engine.
+
+`sample_fn = Sampler(transport).sample_ode(...)` returns a bound `ode.sample` exactly like the reference; when
+`sample_fn(x, model.forward_with_cfg, **kw)` (or `model.forward`) is called with a bound method of the B200
+`LightningDiT`, a velocity model and a fixed-grid method, the whole loop runs natively in
+libvavae_b200.so (no per-step host sync, no trajectory buffer).  Any other callable is integrated by a
+generic fixed-grid loop that only calls `model(x, t, **kw)`.
+"""
+from __future__ import annotations
+
+import enum
+
+import torch as th
+
+
+class ModelType(enum.Enum):
+    NOISE = enum.auto()
+    SCORE = enum.auto()
+    VELOCITY = enum.auto()
+
+
+class PathType(enum.Enum):
+    LINEAR = enum.auto()
+    GVP = enum.auto()
+    VP = enum.auto()
+
+
+class WeightType(enum.Enum):
+    NONE = enum.auto()
+    VELOCITY = enum.auto()
+    LIKELIHOOD = enum.auto()
+
+
+class Transport:
+    """Sampling-side state of transport/transport.py:40-111."""
+
+    def __init__(self, *, model_type, path_type, loss_type, train_eps, sample_eps, use_cosine_loss=False,
+                 use_lognorm=False, partitial_train=None, partial_ratio=1.0, shift_lg=False):
+        self.loss_type = loss_type
+        self.model_type = model_type
+        self.path_type = path_type
+        self.train_eps = train_eps
+        self.sample_eps = sample_eps
+        self.use_cosine_loss = use_cosine_loss
+        self.use_lognorm = use_lognorm
+        self.partitial_train = partitial_train
+        self.partial_ratio = partial_ratio
+        self.shift_lg = shift_lg
+
+    def check_interval(self, train_eps, sample_eps, *, diffusion_form="SBDM", sde=False, reverse=False, eval=False,
+                       last_step_size=0.0):
+        """transport/transport.py:84-111."""
+        t0, t1 = 0, 1
+        eps = train_eps if not eval else sample_eps
+        if self.path_type == PathType.VP:
+            t1 = 1 - eps if (not sde or last_step_size == 0) else 1 - last_step_size
+        elif self.path_type in (PathType.LINEAR, PathType.GVP) and (self.model_type != ModelType.VELOCITY or sde):
+            t0 = eps if (diffusion_form == "SBDM" and sde) or self.model_type != ModelType.VELOCITY else 0
+            t1 = 1 - eps if (not sde or last_step_size == 0) else 1 - last_step_size
+        if reverse:
+            t0, t1 = 1 - t0, 1 - t1
+        return t0, t1
+
+    def get_drift(self):
+        """transport/transport.py:218-250; only the velocity parameterisation is on the engine's path."""
+        if self.model_type != ModelType.VELOCITY:
+            raise NotImplementedError("the B200 sampling engine covers prediction='velocity' only "
+                                      "(every reference config uses it; noise/score drifts are out of scope)")
+
+        def body_fn(x, t, model, **model_kwargs):
+            model_output = model(x, t, **model_kwargs)
+            assert model_output.shape == x.shape, "Output shape from ODE solver must match input shape"
+            return model_output
+        body_fn.is_plain_velocity = True
+        return body_fn
+
+    def training_losses(self, *a, **k):
+        raise NotImplementedError("training is out of scope for the B200 sampling engine")
+
+
+def create_transport(path_type="Linear", prediction="velocity", loss_weight=None, train_eps=None, sample_eps=None,
+                     use_cosine_loss=None, use_lognorm=None, partitial_train=None, partial_ratio=1.0, shift_lg=False):
+    """transport/__init__.py:3-72 (same arguments, same epsilon rules)."""
+    model_type = {"noise": ModelType.NOISE, "score": ModelType.SCORE}.get(prediction, ModelType.VELOCITY)
+    loss_type = {"velocity": WeightType.VELOCITY, "likelihood": WeightType.LIKELIHOOD}.get(loss_weight, WeightType.NONE)
+    path = {"Linear": PathType.LINEAR, "GVP": PathType.GVP, "VP": PathType.VP}[path_type]
+    if path == PathType.VP:
+        train_eps, sample_eps = (1e-5 if train_eps is None else train_eps), (1e-3 if train_eps is None else sample_eps)
+    elif path in (PathType.GVP, PathType.LINEAR) and model_type != ModelType.VELOCITY:
+        train_eps, sample_eps = (1e-3 if train_eps is None else train_eps), (1e-3 if train_eps is None else sample_eps)
+    else:
+        train_eps, sample_eps = 0, 0
+    return Transport(model_type=model_type, path_type=path, loss_type=loss_type, train_eps=train_eps,
+                     sample_eps=sample_eps, use_cosine_loss=use_cosine_loss, use_lognorm=use_lognorm,
+                     partitial_train=partitial_train, partial_ratio=partial_ratio, shift_lg=shift_lg)
+
+
+class LazyTrajectory:
+    """What the native sampler returns in place of the reference's (num_steps, *x.shape) tensor
+    (inference.py:216 only ever takes `[-1]`): the final state, indexable by -1 / num_steps-1."""
+
+    def __init__(self, final, num_steps, trace=None):
+        self._final = final
+        self.num_steps = num_steps
+        self.velocity_trace = trace
+        self.shape = (num_steps,) + tuple(final.shape)
+
+    def __len__(self):
+        return self.num_steps
+
+    def __getitem__(self, idx):
+        if isinstance(idx, int) and idx in (-1, self.num_steps - 1):
+            return self._final
+        raise IndexError("the native sampler keeps only the final state of the trajectory (what every reference "
+                         "caller uses); pass keep_trajectory=True to Sampler.sample_ode for intermediate points")
+
+
+def _time_grid(t0, t1, num_steps, timestep_shift):
+    """transport/integrators.py:94-101, same ops so the fp32 grid is bit-identical."""
+    t = th.linspace(t0, t1, num_steps)
+    if timestep_shift > 0:
+        def compute_tm(t_n, s):
+            return (s * t_n) / (1 + (s - 1) * t_n)
+        t = th.tensor([compute_tm(t_n, timestep_shift) for t_n in t])
+    return t
+
+
+class ode:
+    """transport/integrators.py:77-126."""
+
+    def __init__(self, drift, *, t0, t1, sampler_type, num_steps, atol, rtol, timestep_shift, keep_trajectory=False,
+                 native_ok=True):
+        assert t0 < t1, "ODE sampler has to be in forward time"
+        self.drift = drift
+        self.t = _time_grid(t0, t1, num_steps, timestep_shift)
+        self.atol, self.rtol = atol, rtol
+        self.sampler_type = sampler_type
+        self.keep_trajectory = keep_trajectory
+        self.native_ok = native_ok
+
+    def _native_target(self, model):
+        from .lightningdit import LightningDiT
+        owner = getattr(model, "__self__", None)
+        if not isinstance(owner, LightningDiT) or not self.native_ok or self.keep_trajectory:
+            return None, None
+        name = getattr(model, "__name__", "")
+        if name in ("forward_with_cfg", "forward"):
+            return owner, name
+        return None, None
+
+    def sample(self, x, model, **model_kwargs):
+        method = self.sampler_type
+        if method not in ("euler", "heun", "heun2"):
+            raise NotImplementedError(f"sampling_method={method!r}: the B200 engine implements the fixed-grid "
+                                      "solvers 'euler' and 'heun'; adaptive dopri5 is a planned follow-up "
+                                      "(SURVEY.md section 8f)")
+        owner, name = self._native_target(model)
+        if owner is not None:
+            eng = owner.engine()
+            owner._require_eval()
+            if name == "forward_with_cfg":
+                final = eng.sample_ode(x, model_kwargs["y"], self.t, method, True, model_kwargs["cfg_scale"],
+                                       model_kwargs.get("cfg_interval"), model_kwargs.get("cfg_interval_start"), 3)
+            else:
+                final = eng.sample_ode(x, model_kwargs["y"], self.t, method, False)
+            return LazyTrajectory(final, len(self.t))
+        # generic fixed-grid loop (torchdiffeq fixed-grid semantics: one step per interval, solution[j] = y_j)
+        device = x.device
+        t = self.t.to(device)
+        ys, y = [x], x
+        for j in range(len(t) - 1):
+            t0, t1 = t[j], t[j + 1]
+            dt = t1 - t0
+            k1 = self.drift(y, th.ones(y.size(0)).to(device) * t0, model, **model_kwargs)
+            if method == "euler":
+                y = y + dt * k1
+            else:
+                k2 = self.drift(y + dt * k1, th.ones(y.size(0)).to(device) * t1, model, **model_kwargs)
+                y = y + (dt * 0.5) * (k1 + k2)
+            ys.append(y)
+        return th.stack(ys)
+
+
+class Sampler:
+    """transport/transport.py:270-283,398-443 (ODE side)."""
+
+    def __init__(self, transport):
+        self.transport = transport
+        self.drift = self.transport.get_drift()
+
+    def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False,
+                   timestep_shift=0.0, keep_trajectory=False):
+        native_ok = not reverse
+        if reverse:
+            def drift(x, t, model, **kwargs):
+                return self.drift(x, th.ones_like(t) * (1 - t), model, **kwargs)
+        else:
+            drift = self.drift
+        t0, t1 = self.transport.check_interval(self.transport.train_eps, self.transport.sample_eps, sde=False, eval=True,
+                                               reverse=reverse, last_step_size=0.0)
+        _ode = ode(drift=drift, t0=t0, t1=t1, sampler_type=sampling_method, num_steps=num_steps, atol=atol, rtol=rtol,
+                   timestep_shift=timestep_shift, keep_trajectory=keep_trajectory, native_ok=native_ok)
+        return _ode.sample
+
+    def sample_sde(self, *a, **k):
+        raise NotImplementedError("SDE sampling is out of scope for the B200 ODE sampling engine")
+
+    def sample_ode_likelihood(self, *a, **k):
+        raise NotImplementedError("likelihood evaluation is out of scope for the B200 ODE sampling engine")
