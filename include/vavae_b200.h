@@ -110,6 +110,14 @@ uint64_t vavae_device_bytes(const vavae_engine_t* e);
 const char* vavae_last_error(void);
 int vavae_abi_version(void);
 
+/* Live per-kernel measurement for bench.py's roofline: between profile_begin(kernel) and profile_end every
+ * launch of that kernel class ("gemm_qkv", "attention", "gemm_proj", "gemm_w12", "gemm_w3", "norm_modulate")
+ * is bracketed by a CUDA event pair on the launching stream.  profile_end synchronises those events and
+ * returns their summed duration, the launch count and the summed algorithmic work (FLOPs, or bytes for
+ * norm_modulate). */
+int vavae_profile_begin(vavae_engine_t* e, const char* kernel);
+int vavae_profile_end(vavae_engine_t* e, double* total_ms, int64_t* launches, double* total_work);
+
 /* ---- kernel-level test / measurement entry points (tests/ and bench.py; not needed by a drop-in) ---- */
 
 /* C[M,N] (f32) = A[M,K] (bf16) * W[N,K]^T (bf16) + bias[N] (f32, may be NULL) on the tcgen05 GEMM. */

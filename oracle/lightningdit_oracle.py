@@ -168,6 +168,20 @@ def init_state_dict(cfg: DiTConfig, seed: int = 0, std: float = 0.02) -> dict:
 
 
 # ----------------------------------------------------------------------------- primitives
+# Optional emulation of the engine's bf16 rounding points (GEMM / attention operands and the tensors the
+# engine stores in bf16); everything else stays fp32 exactly like the engine.  Used only to *explain* the
+# bf16-mode error budget in tests; parity bars are always measured against the plain fp32 path above.
+BF16_EMULATION = False
+
+
+def _q(x):
+    return x.bfloat16().float() if BF16_EMULATION else x
+
+
+def _lin(x, w, b):
+    return F.linear(_q(x), _q(w), b)
+
+
 def rms_norm(x, w, eps=1e-6):
     """models/rmsnorm.py:63,76-77 -- fp32 statistics, learnable weight."""
     xf = x.float()
@@ -215,7 +229,7 @@ def attention(cfg, sd, pre, x):
     """models/lightningdit.py:66-91."""
     B, T, D = x.shape
     H, hd = cfg.num_heads, cfg.head_dim
-    qkv = F.linear(x, sd[pre + "qkv.weight"], sd[pre + "qkv.bias"])
+    qkv = _lin(x, sd[pre + "qkv.weight"], sd[pre + "qkv.bias"])
     qkv = qkv.reshape(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
     if cfg.use_qknorm:
@@ -224,26 +238,27 @@ def attention(cfg, sd, pre, x):
         cos, sin = sd["feat_rope.freqs_cos"], sd["feat_rope.freqs_sin"]
         q = q * cos + rotate_half(q) * sin
         k = k * cos + rotate_half(k) * sin
+    q, k, v = _q(q), _q(k), _q(v)
     att = (q * hd ** -0.5) @ k.transpose(-2, -1)      # manual branch :82-86 == SDPA :77-80
     att = att.softmax(dim=-1)
-    o = (att @ v).transpose(1, 2).reshape(B, T, D)
-    return F.linear(o, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
+    o = (_q(att) @ v).transpose(1, 2).reshape(B, T, D)
+    return _lin(o, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
 
 
 def mlp(cfg, sd, pre, x):
     if cfg.use_swiglu:
         # models/swiglu_ffn.py:31-36 -- x1 (first S columns) is the SiLU-gated half
-        x12 = F.linear(x, sd[pre + "w12.weight"], sd[pre + "w12.bias"])
+        x12 = _lin(x, sd[pre + "w12.weight"], sd[pre + "w12.bias"])
         x1, x2 = x12.chunk(2, dim=-1)
-        return F.linear(F.silu(x1) * x2, sd[pre + "w3.weight"], sd[pre + "w3.bias"])
-    h = F.gelu(F.linear(x, sd[pre + "fc1.weight"], sd[pre + "fc1.bias"]), approximate="tanh")
-    return F.linear(h, sd[pre + "fc2.weight"], sd[pre + "fc2.bias"])
+        return _lin(F.silu(x1) * x2, sd[pre + "w3.weight"], sd[pre + "w3.bias"])
+    h = F.gelu(_lin(x, sd[pre + "fc1.weight"], sd[pre + "fc1.bias"]), approximate="tanh")
+    return _lin(h, sd[pre + "fc2.weight"], sd[pre + "fc2.bias"])
 
 
 def block(cfg, sd, i, x, c):
     """models/lightningdit.py:239-250."""
     pre = f"blocks.{i}."
-    m = F.linear(F.silu(c), sd[pre + "adaLN_modulation.1.weight"], sd[pre + "adaLN_modulation.1.bias"])
+    m = _lin(F.silu(c), sd[pre + "adaLN_modulation.1.weight"], sd[pre + "adaLN_modulation.1.bias"])
     if cfg.wo_shift:
         scale_msa, gate_msa, scale_mlp, gate_mlp = m.chunk(4, dim=1)
         shift_msa = shift_mlp = None
@@ -276,10 +291,10 @@ def forward(cfg: DiTConfig, sd: dict, x, t, y):
     for i in range(cfg.depth):
         tok = block(cfg, sd, i, tok, c)
     # FinalLayer, models/lightningdit.py:267-272 (shift first)
-    shift, scale = F.linear(F.silu(c), sd["final_layer.adaLN_modulation.1.weight"],
-                            sd["final_layer.adaLN_modulation.1.bias"]).chunk(2, dim=1)
+    shift, scale = _lin(F.silu(c), sd["final_layer.adaLN_modulation.1.weight"],
+                        sd["final_layer.adaLN_modulation.1.bias"]).chunk(2, dim=1)
     tok = modulate(_norm_block(cfg, sd, "final_layer.norm_final", tok), shift, scale)
-    tok = F.linear(tok, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])
+    tok = _lin(tok, sd["final_layer.linear.weight"], sd["final_layer.linear.bias"])
     out = unpatchify(cfg, tok)
     if cfg.learn_sigma:
         out, _ = out.chunk(2, dim=1)
@@ -295,7 +310,7 @@ def forward_with_cfg(cfg, sd, x, t, y, cfg_scale, cfg_interval=None, cfg_interva
     eps, rest = out[:, :cfg_channels], out[:, cfg_channels:]
     cond, uncond = torch.split(eps, len(eps) // 2, dim=0)
     half_eps = uncond + cfg_scale * (cond - uncond)
-    if cfg_interval is True and float(t[0]) < cfg_interval_start:
+    if cfg_interval is True and bool(t[0] < cfg_interval_start):   # fp32 tensor vs python scalar, as in :437-439
         half_eps = cond
     return torch.cat([torch.cat([half_eps, half_eps], dim=0), rest], dim=1)
 

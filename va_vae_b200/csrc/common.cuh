@@ -102,6 +102,9 @@ struct NormModArgs {
   int ldo;
   int M, D, T;
   int out_bf16;
+  int split3;  // bf16 only: write [hi | lo | hi] (3*D columns) so a bf16 GEMM against [Whi | Whi | Wlo]
+               // reproduces the fp32 product to ~2^-17 (used for the final layer, whose rounding error
+               // would otherwise be amplified by the CFG scale)
 };
 void launch_norm_modulate(const NormModArgs& a, cudaStream_t s);
 

@@ -40,6 +40,11 @@ struct vavae_engine {
   std::vector<void*> owned;  // everything cudaMalloc'ed by the engine
   uint64_t bytes = 0;
   LaunchCounter counter;
+  // live per-kernel profiling (bench.py roofline): CUDA event pairs around every launch of one kernel class
+  int prof_kernel = -1;
+  std::vector<cudaEvent_t> prof_ev;  // pairs: [2i] start, [2i+1] stop
+  size_t prof_used = 0;
+  double prof_work = 0.0;
 
   // packed (both modes)
   float* embed_wT = nullptr;  // [C*p*p, D]
@@ -57,6 +62,7 @@ struct vavae_engine {
   float *A_f = nullptr, *QKV_f = nullptr, *q_f = nullptr, *k_f = nullptr, *v_f = nullptr, *O_f = nullptr, *Y_f = nullptr,
         *U_f = nullptr, *Hh_f = nullptr, *Yfin_f = nullptr;
   // bf16 path
+  bf16* A3_h = nullptr;  // [M, 3D] split-bf16 operand of the final linear
   bf16 *A_h = nullptr, *q_h = nullptr, *k_h = nullptr, *vt_h = nullptr, *O_h = nullptr, *Hh_h = nullptr;
 
   // sampler state (lazily sized)
@@ -104,6 +110,35 @@ struct vavae_engine {
 };
 
 // --------------------------------------------------------------------------------------------- helpers
+enum ProfKernel { PK_QKV = 0, PK_ATTN = 1, PK_PROJ = 2, PK_W12 = 3, PK_W3 = 4, PK_NORM = 5, PK_ODE = 6, PK_COUNT = 7 };
+static const char* kProfNames[PK_COUNT] = {"gemm_qkv", "attention", "gemm_proj", "gemm_w12", "gemm_w3", "norm_modulate",
+                                           "ode_update"};
+constexpr size_t kProfMaxPairs = 1 << 16;
+
+// RAII: records an event pair around one launch when its kernel class is being profiled
+struct ProfScope {
+  vavae_engine* e;
+  cudaStream_t s;
+  bool on;
+  ProfScope(vavae_engine* e_, int kernel, double work, cudaStream_t s_) : e(e_), s(s_), on(false) {
+    if (e->prof_kernel != kernel || e->prof_used >= kProfMaxPairs) return;
+    if (e->prof_ev.size() < 2 * (e->prof_used + 1)) {
+      cudaEvent_t a, b;
+      VV_CUDA(cudaEventCreate(&a));
+      VV_CUDA(cudaEventCreate(&b));
+      e->prof_ev.push_back(a);
+      e->prof_ev.push_back(b);
+    }
+    VV_CUDA(cudaEventRecord(e->prof_ev[2 * e->prof_used], s));
+    e->prof_work += work;
+    on = true;
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(e->prof_ev[2 * e->prof_used + 1], s);
+    e->prof_used++;
+  }
+};
 static std::string blk(int i, const char* s) { return "blocks." + std::to_string(i) + "." + s; }
 
 __global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
@@ -121,6 +156,19 @@ __global__ void k_pack_rows_bf16(const float* __restrict__ in, bf16* __restrict_
   int src = r;
   if (interleave_S > 0) src = (r & 1) ? interleave_S + (r >> 1) : (r >> 1);
   out[(size_t)r * ldo + c] = __float2bfloat16_rn(in[(size_t)src * K + c]);
+}
+// final linear weight as [hi | hi | lo] along K (pairs with the [hi | lo | hi] activation layout)
+__global__ void k_pack_split3(const float* __restrict__ in, bf16* __restrict__ out, int rows, int K) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * K) return;
+  int r = (int)(idx / K), c = (int)(idx % K);
+  float w = in[idx];
+  bf16 hi = __float2bfloat16_rn(w);
+  bf16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  bf16* o = out + (size_t)r * 3 * K;
+  o[c] = hi;
+  o[K + c] = hi;
+  o[2 * K + c] = lo;
 }
 __global__ void k_interleave_bias(const float* __restrict__ in, float* __restrict__ out, int S) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +215,6 @@ static void derive(vavae_engine* e) {
   if (!e->fp32) {
     VV_CHECK(e->D % 16 == 0 && e->hd % 8 == 0 && e->hd <= 128, "bf16 path: hidden % 16, head_dim % 8, head_dim <= 128");
     VV_CHECK(e->T % 8 == 0, "bf16 path: token count must be a multiple of 8");
-    VV_CHECK(e->S % 2 == 0, "bf16 path: mlp hidden must be even");
   }
 }
 
@@ -254,9 +301,11 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
       lw.proj = e->alloc<bf16>((size_t)D * D);
       pack_bf16(e, e->W(blk(i, "attn.proj.weight")).d, lw.proj, D, D, D, 0, s);
       if (c.use_swiglu) {
-        lw.w1 = e->alloc<bf16>((size_t)2 * S * D);
+        // N is rounded up to a multiple of 4 with zero rows / zero bias so the epilogue can work on float4 groups
+        const int N12 = ((2 * S + 3) / 4) * 4;
+        lw.w1 = e->alloc<bf16>((size_t)N12 * D, true);
         pack_bf16(e, e->W(blk(i, "mlp.w12.weight")).d, lw.w1, 2 * S, D, D, S, s);
-        lw.b1 = e->alloc<float>(2 * S);
+        lw.b1 = e->alloc<float>(N12, true);
         k_interleave_bias<<<cdiv(2 * S, 256), 256, 0, s>>>(e->W(blk(i, "mlp.w12.bias")).d, lw.b1, S);
         VV_LAUNCH_CHECK();
         lw.w2 = e->alloc<bf16>((size_t)D * e->Spad, true);
@@ -269,8 +318,9 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
         pack_bf16(e, e->W(blk(i, "mlp.fc2.weight")).d, lw.w2, D, S, e->Spad, 0, s);
       }
     }
-    e->final_w_h = e->alloc<bf16>((size_t)e->Pout * D);
-    pack_bf16(e, e->W("final_layer.linear.weight").d, e->final_w_h, e->Pout, D, D, 0, s);
+    e->final_w_h = e->alloc<bf16>((size_t)e->Pout * 3 * D);
+    k_pack_split3<<<cdiv(e->Pout * D, 256), 256, 0, s>>>(e->W("final_layer.linear.weight").d, e->final_w_h, e->Pout, D);
+    VV_LAUNCH_CHECK();
     VV_CUDA(cudaStreamSynchronize(s));
     // the fp32 originals of the big matrices are no longer needed on the bf16 path
     for (int i = 0; i < L; ++i) {
@@ -312,6 +362,7 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
   } else {
     e->sc_h = e->alloc<bf16>((size_t)R * D);
     e->A_h = e->alloc<bf16>(M * D);
+    e->A3_h = e->alloc<bf16>(M * 3 * D);
     // padding columns d in [hd, hdp) of q/k and rows [hd, hdv) of v^T stay zero forever (never written)
     e->q_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
     e->k_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
@@ -340,11 +391,14 @@ static ModOff mod_offsets(const vavae_engine* e, int layer) {
   return o;
 }
 
-static void norm_mod(vavae_engine* e, const float* w, int shift_off, int scale_off, int M, cudaStream_t s) {
+static void norm_mod(vavae_engine* e, const float* w, int shift_off, int scale_off, int M, cudaStream_t s,
+                     bool split3 = false) {
   NormModArgs n;
   n.X = e->X; n.w = w; n.mod = e->mod; n.mod_ld = e->NM; n.shift_off = shift_off; n.scale_off = scale_off;
-  n.out = e->fp32 ? (void*)e->A_f : (void*)e->A_h; n.ldo = e->D; n.M = M; n.D = e->D; n.T = e->T;
+  n.out = e->fp32 ? (void*)e->A_f : (split3 ? (void*)e->A3_h : (void*)e->A_h);
+  n.ldo = split3 ? 3 * e->D : e->D; n.M = M; n.D = e->D; n.T = e->T;
   n.out_bf16 = e->fp32 ? 0 : 1;
+  n.split3 = split3 ? 1 : 0;
   launch_norm_modulate(n, s);
 }
 
@@ -414,7 +468,10 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       }
     }
     // ---- attention branch
-    norm_mod(e, n1, mo.shift_msa, mo.scale_msa, M, s);
+    {
+      ProfScope ps(e, PK_NORM, (double)M * D * (e->fp32 ? 8.0 : 6.0), s);
+      norm_mod(e, n1, mo.shift_msa, mo.scale_msa, M, s);
+    }
     if (e->fp32) {
       gemm32(e->A_f, D, e->W(blk(i, "attn.qkv.weight")).d, e->W(blk(i, "attn.qkv.bias")).d, e->QKV_f, 3 * D, M, 3 * D, D,
              F32_EPI_NONE, s);
@@ -431,14 +488,23 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].qkv, D, M, 3 * D, D, TC_EPI_QKV, e->W(blk(i, "attn.qkv.bias")).d);
       a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
       a.kn_b = knb; a.qk_rms = c.use_rmsnorm; a.H = H; a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
-      launch_gemm_tc(a, s);
+      {
+        ProfScope ps(e, PK_QKV, 2.0 * M * 3.0 * D * D, s);
+        launch_gemm_tc(a, s);
+      }
       TcAttnArgs at;
       at.q = e->q_h; at.k = e->k_h; at.vt = e->vt_h; at.out = e->O_h; at.B = rows; at.H = H; at.T = T; at.hd = hd;
       at.hdp = e->hdp; at.hdv = e->hdv;
-      launch_attention_tc(at, s);
+      {
+        ProfScope ps(e, PK_ATTN, 4.0 * rows * (double)H * T * T * hd, s);
+        launch_attention_tc(at, s);
+      }
       TcGemmArgs pr = tc_args(e->O_h, D, e->lw[i].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(i, "attn.proj.bias")).d);
       pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NM; pr.gate_off = mo.gate_msa; pr.T = T;
-      launch_gemm_tc(pr, s);
+      {
+        ProfScope ps(e, PK_PROJ, 2.0 * M * (double)D * D, s);
+        launch_gemm_tc(pr, s);
+      }
     }
     // ---- MLP branch
     norm_mod(e, n2, mo.shift_mlp, mo.scale_mlp, M, s);
@@ -458,23 +524,28 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       launch_gated_residual_f32(e->X, e->Y_f, e->mod, e->NM, mo.gate_mlp, M, D, T, s);
     } else {
       if (c.use_swiglu) {
-        TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, 2 * S, D, TC_EPI_SWIGLU, e->lw[i].b1);
+        TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, ((2 * S + 3) / 4) * 4, D, TC_EPI_SWIGLU, e->lw[i].b1);
         a.out = e->Hh_h; a.ldo = e->Spad;
+        ProfScope ps(e, PK_W12, 2.0 * M * 2.0 * S * D, s);
         launch_gemm_tc(a, s);
       } else {
         TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, S, D, TC_EPI_GELU_BF16, e->lw[i].b1);
         a.out = e->Hh_h; a.ldo = e->Spad;
+        ProfScope ps(e, PK_W12, 2.0 * M * (double)S * D, s);
         launch_gemm_tc(a, s);
       }
       const float* b2 = e->W(blk(i, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d;
       TcGemmArgs a = tc_args(e->Hh_h, e->Spad, e->lw[i].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL, b2);
       a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NM; a.gate_off = mo.gate_mlp; a.T = T;
-      launch_gemm_tc(a, s);
+      {
+        ProfScope ps(e, PK_W3, 2.0 * M * (double)S * D, s);
+        launch_gemm_tc(a, s);
+      }
     }
   }
   // ---- final layer (lightningdit.py:267-272): shift first, then scale
   const int fbase = L * e->nmod * D;
-  norm_mod(e, c.use_rmsnorm ? e->W("final_layer.norm_final.weight").d : nullptr, fbase, fbase + D, M, s);
+  norm_mod(e, c.use_rmsnorm ? e->W("final_layer.norm_final.weight").d : nullptr, fbase, fbase + D, M, s, !e->fp32);
   if (e->fp32) {
     gemm32(e->A_f, D, e->W("final_layer.linear.weight").d, e->W("final_layer.linear.bias").d, e->Yfin_f, e->Pout, M,
            e->Pout, D, F32_EPI_NONE, s);
@@ -483,7 +554,9 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
     u.rm = rm;
     launch_unpatchify(u, s);
   } else {
-    TcGemmArgs a = tc_args(e->A_h, D, e->final_w_h, D, M, e->Pout, D, TC_EPI_FINAL, e->W("final_layer.linear.bias").d);
+    // split-bf16 product: [hi|lo|hi] x [Whi|Whi|Wlo] = hi*Whi + lo*Whi + hi*Wlo  (K = 3D), fp32-grade output
+    TcGemmArgs a = tc_args(e->A3_h, 3 * D, e->final_w_h, 3 * D, M, e->Pout, 3 * D, TC_EPI_FINAL,
+                           e->W("final_layer.linear.bias").d);
     a.out = out; a.T = T; a.p = e->p; a.Cout = e->Cout; a.Ckeep = e->Ckeep; a.img = e->img; a.rm = rm;
     launch_gemm_tc(a, s);
   }
@@ -568,12 +641,17 @@ static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const 
     o.t = e->tgrid_dev + j;
     o.trace = out_trace ? out_trace + (size_t)(eval++) * batch * per : nullptr;
     o.stage = method == VAVAE_ODE_EULER ? 0 : 1;
-    launch_ode_update(o, s);
+    const double ode_bytes = (double)batch * per * 4.0 * 3.0;  // read v, read x, write x (Heun stages move a little more)
+    {
+      ProfScope ps(e, PK_ODE, ode_bytes, s);
+      launch_ode_update(o, s);
+    }
     if (method == VAVAE_ODE_HEUN) {
       eval_model(e->sxp, j + 1);
       o.t = e->tgrid_dev + j + 1;
       o.trace = out_trace ? out_trace + (size_t)(eval++) * batch * per : nullptr;
       o.stage = 2;
+      ProfScope ps(e, PK_ODE, ode_bytes, s);
       launch_ode_update(o, s);
     }
   }
@@ -721,6 +799,37 @@ int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t*
 uint64_t vavae_launch_count(const vavae_engine_t* e) { return e ? e->counter.n : 0; }
 uint64_t vavae_device_bytes(const vavae_engine_t* e) { return e ? e->bytes : 0; }
 
+int vavae_profile_begin(vavae_engine_t* e, const char* kernel) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e, "null engine");
+  e->prof_kernel = -1;
+  e->prof_used = 0;
+  e->prof_work = 0.0;
+  if (kernel) {
+    for (int i = 0; i < PK_COUNT; ++i)
+      if (std::string(kernel) == kProfNames[i]) e->prof_kernel = i;
+    VV_CHECK(e->prof_kernel >= 0, std::string("profile_begin: unknown kernel ") + kernel);
+  }
+  VV_API_END()
+}
+
+int vavae_profile_end(vavae_engine_t* e, double* total_ms, int64_t* launches, double* total_work) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && total_ms && launches && total_work, "null argument");
+  double ms = 0.0;
+  for (size_t i = 0; i < e->prof_used; ++i) {
+    float t = 0.f;
+    VV_CUDA(cudaEventSynchronize(e->prof_ev[2 * i + 1]));
+    VV_CUDA(cudaEventElapsedTime(&t, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]));
+    ms += t;
+  }
+  *total_ms = ms;
+  *launches = (int64_t)e->prof_used;
+  *total_work = e->prof_work;
+  e->prof_kernel = -1;
+  VV_API_END()
+}
+
 // ---- kernel-level test entry points -----------------------------------------------------------
 int vavae_test_gemm_bf16(const void* A, const void* Wt, const float* bias, float* Cc, int M, int N, int K, void* stream) {
   try {
@@ -789,7 +898,7 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     VV_CHECK(c.use_swiglu, "gemm_w12 needs use_swiglu");
     *work = 2.0 * M * 2.0 * S * D;
     fn = [&] {
-      TcGemmArgs a = tc_args(e->A_h, D, e->lw[0].w1, D, M, 2 * S, D, TC_EPI_SWIGLU, e->lw[0].b1);
+      TcGemmArgs a = tc_args(e->A_h, D, e->lw[0].w1, D, M, ((2 * S + 3) / 4) * 4, D, TC_EPI_SWIGLU, e->lw[0].b1);
       a.out = e->Hh_h; a.ldo = e->Spad;
       launch_gemm_tc(a, s);
     };

@@ -2,7 +2,8 @@
 //   C[M,N] = A[M,K] (bf16, K-major) * W[N,K]^T (bf16, K-major), fp32 accumulation in TMEM.
 //   warp 0      : TMA producer (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BN, K=16 per instruction)
-//   warps 2..5  : epilogue - tcgen05.ld from TMEM (lane quarter = warp%4), fused epilogue, coalesced stores
+//   warps 2..9  : epilogue - tcgen05.ld from TMEM (lane quarter = warp%4, two warps per quarter taking alternate
+//                 column chunks), fused epilogue, smem-staged coalesced stores, residual prefetched a chunk ahead
 // Accumulators are double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1; shared-memory operand tiles run through an N-stage full/empty mbarrier ring.
 #include "gemm_tc.cuh"
@@ -64,10 +65,10 @@ CUtensorMap make_tmap_3d_bf16(const void* base, uint64_t d0, uint64_t d1, uint64
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_MAX_STAGES = 8;
 
-__device__ __forceinline__ float silu_fast(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
@@ -121,7 +122,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = TC_A_BYTES + BN * 128;
   float* staging = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
-  TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(reinterpret_cast<uint8_t*>(staging) + 4 * 32 * (CW + 4) * 4);
+  TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(reinterpret_cast<uint8_t*>(staging) + 8 * 32 * (CW + 4) * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (a.M + TC_BM - 1) / TC_BM;
@@ -138,7 +139,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->tfull[i], 1);
-      ptx::mbar_init(&bars->tempty[i], 128);
+      ptx::mbar_init(&bars->tempty[i], 256);
     }
     ptx::fence_barrier_init();
   }
@@ -202,30 +203,59 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    float* st = staging + (size_t)q * 32 * (CW + 4);
-    constexpr int LPR = CW / 4;   // lanes per row in the row-wise pass
-    constexpr int RPP = 32 / LPR; // rows per pass
+    // ------------------------------------------------------------------ epilogue warps (8: two per TMEM lane quarter)
+    const int q = warp & 3;            // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter take alternate column chunks
+    float* st = staging + (size_t)(warp - 2) * 32 * (CW + 4);
+    constexpr int LPR = CW / 4;    // lanes per row in the row-wise pass
+    constexpr int RPP = 32 / LPR;  // rows per pass
+    const int prow = lane / LPR;   // row (within a pass) and column group this lane owns in the row-wise pass
+    const int pcc = (lane % LPR) * 4;
+    const bool rows_one_sample = (a.T % 32) == 0;  // the warp's 32 rows are consecutive tokens of one sample
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int m0 = m_blk * TC_BM, n0 = n_blk * BN;
+      const int wrow0 = m0 + q * 32;     // first row of this warp
+      const int my_row = wrow0 + lane;   // thread == row domain
+      int n_chunks = (min(BN, a.N - n0) + CW - 1) / CW;
+
+      // ---- prefetch for the gated-residual epilogue: the fp32 residual tile is loaded one chunk ahead so the
+      //      HBM/L2 latency overlaps the TMEM drain of the previous chunk (and the wait for the MMA)
+      float4 xpre[LPR];
+      auto prefetch_x = [&](int c) {
+        if (EPI == TC_EPI_GATED_RESIDUAL) {
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) {
+            const int row = wrow0 + ps * RPP + prow, col = n0 + c * CW + pcc;
+            xpre[ps] = (c < n_chunks && row < a.M && col < a.N)
+                           ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.out) + (size_t)row * a.ldo + col)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      prefetch_x(half);
+
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
-      const int my_row = m0 + q * 32 + lane;  // thread == row domain
 
       // qk-norm statistics are computed on demand per head (thread == row domain)
       float qk_mean = 0.f, qk_rstd = 1.f;
       int qk_head = -1;
 
-      for (int c0 = 0; c0 < BN; c0 += CW) {
-        if (n0 + c0 >= a.N) break;
+      for (int c = half; c < n_chunks; c += 2) {
+        const int c0 = c * CW;
         uint32_t r[CW];
         if (CW == 32) ptx::tmem_ld_x32(tbase + c0, r);
         else ptx::tmem_ld_x16(tbase + c0, r);
+        float4 xcur[LPR];
+        if (EPI == TC_EPI_GATED_RESIDUAL) {
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) xcur[ps] = xpre[ps];
+          prefetch_x(c + 2);
+        }
         ptx::tmem_ld_wait();
 
         if (EPI == TC_EPI_FINAL) {
@@ -240,21 +270,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int j = 0; j < CW; ++j) {
               const int col = n0 + c0 + j;
               if (col < a.N) {
-                const int c = col % a.Cout, ab = col / a.Cout, pa = ab / a.p, pb = ab % a.p;
-                if (c < a.Ckeep)
-                  ob[((size_t)c * a.img + ti * a.p + pa) * a.img + tj * a.p + pb] = __uint_as_float(r[j]) + a.bias[col];
+                const int ch = col % a.Cout, ab = col / a.Cout, pa = ab / a.p, pb = ab % a.p;
+                if (ch < a.Ckeep)
+                  ob[((size_t)ch * a.img + ti * a.p + pa) * a.img + tj * a.p + pb] = __uint_as_float(r[j]) + a.bias[col];
               }
             }
           }
           continue;
         }
 
+        bool v_chunk = false;
         if (EPI == TC_EPI_QKV) {
           const int colc = n0 + c0;
           const int D = a.H * a.hd;
           const int which = colc / D;
-          if (which == 2) {
-            // V: store transposed (B,H,hdv,T): lanes = consecutive tokens -> 64 contiguous bytes per store
+          v_chunk = which == 2;
+          if (v_chunk && !(rows_one_sample && CW == 32)) {
+            // generic V path: transposed scalar stores (B,H,hdv,T); lanes = consecutive tokens
             if (my_row < a.M) {
               const int b = my_row / a.T, t = my_row % a.T;
 #pragma unroll
@@ -269,9 +301,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             continue;
           }
-          // q / k: bias (+ optional qk-norm) in the thread == row domain, RoPE + store in the row-wise pass
-          const float* nw = which == 0 ? a.qn_w : a.kn_w;
-          const float* nb = which == 0 ? a.qn_b : a.kn_b;
+          // q / k (and fast-path v): bias (+ optional qk-norm) in the thread == row domain
+          const float* nw = which == 0 ? a.qn_w : (which == 1 ? a.kn_w : nullptr);
+          const float* nb = which == 0 ? a.qn_b : (which == 1 ? a.kn_b : nullptr);
 #pragma unroll
           for (int j = 0; j < CW; ++j) {
             const int col = colc + j;
@@ -288,7 +320,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
 
-        // ---- stage the 32 x CW fp32 block in shared memory, then store row-wise (coalesced)
+        // ---- stage the 32 x CW fp32 block in shared memory (thread == row), then work row-wise (coalesced)
         __syncwarp();
 #pragma unroll
         for (int j4 = 0; j4 < CW / 4; ++j4)
@@ -296,18 +328,100 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]), __uint_as_float(r[j4 * 4 + 2]),
                           __uint_as_float(r[j4 * 4 + 3]));
         __syncwarp();
+
+        if (EPI == TC_EPI_QKV && v_chunk) {
+          // V^T fast path: lane owns head-dim column d and 8 consecutive tokens -> one 16-byte store;
+          // a warp instruction writes 8 columns x 64 contiguous bytes of (B,H,hdv,T)
+          const int D = a.H * a.hd;
+          const int b = wrow0 / a.T, t0 = wrow0 % a.T;
+          const int tg = lane & 3;
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int j = ps * 8 + (lane >> 2);
+            const int col = n0 + c0 + j;
+            if (col < a.N && wrow0 + tg * 8 < a.M) {
+              const int rem = col - 2 * D, h = rem / a.hd, d = rem % a.hd;
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = st[(tg * 8 + e) * (CW + 4) + j];
+              uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              *reinterpret_cast<uint4*>(a.vt + (((size_t)b * a.H + h) * a.hdv + d) * a.T + t0 + tg * 8) = pk;
+            }
+          }
+          continue;
+        }
+
+        const int col = n0 + c0 + pcc;  // this lane's 4 columns in every pass
+        const bool col_ok = col < a.N;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI != TC_EPI_QKV && a.bias && col_ok) bb = *reinterpret_cast<const float4*>(a.bias + col);
+
+        if (EPI == TC_EPI_GATED_RESIDUAL) {
+          // x = x + gate.unsqueeze(1) * f(...)   lightningdit.py:248-249 ; x was prefetched one chunk ahead
+          float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rows_one_sample && col_ok && wrow0 < a.M)
+            g1 = *reinterpret_cast<const float4*>(a.mod + (size_t)(wrow0 / a.T) * a.mod_ld + a.gate_off + col);
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) {
+            const int rr = ps * RPP + prow;
+            const int row = wrow0 + rr;
+            if (row >= a.M || !col_ok) continue;
+            float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + pcc);
+            float4 g = g1;
+            if (!rows_one_sample)
+              g = *reinterpret_cast<const float4*>(a.mod + (size_t)(row / a.T) * a.mod_ld + a.gate_off + col);
+            float4 x = xcur[ps];
+            x.x = fmaf(g.x, v.x + bb.x, x.x); x.y = fmaf(g.y, v.y + bb.y, x.y);
+            x.z = fmaf(g.z, v.z + bb.z, x.z); x.w = fmaf(g.w, v.w + bb.w, x.w);
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = x;
+          }
+          continue;
+        }
+
+        if (EPI == TC_EPI_QKV) {
+          // RoPE: t*cos + rotate_half(t)*sin with (a,b) -> (-b,a) on adjacent pairs; pos_embed.py:38-42,135.
+          // All table loads of the chunk are issued before the first store (no load -> store -> load chains).
+          const int D = a.H * a.hd;
+          const int which = col / D, rem = col - which * D, h = rem / a.hd, d = rem % a.hd;
+          float4 c4[LPR], s4[LPR];
+          if (a.cos) {
+#pragma unroll
+            for (int ps = 0; ps < LPR; ++ps) {
+              const int row = wrow0 + ps * RPP + prow;
+              const int t = row % a.T;
+              const bool ok = row < a.M && col_ok;
+              c4[ps] = ok ? *reinterpret_cast<const float4*>(a.cos + (size_t)t * a.hd + d) : make_float4(1.f, 1.f, 1.f, 1.f);
+              s4[ps] = ok ? *reinterpret_cast<const float4*>(a.sin + (size_t)t * a.hd + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) {
+            const int rr = ps * RPP + prow;
+            const int row = wrow0 + rr;
+            if (row >= a.M || !col_ok) continue;
+            float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + pcc);
+            if (a.cos) {
+              float4 o;
+              o.x = v.x * c4[ps].x - v.y * s4[ps].x;
+              o.y = v.y * c4[ps].y + v.x * s4[ps].y;
+              o.z = v.z * c4[ps].z - v.w * s4[ps].z;
+              o.w = v.w * c4[ps].w + v.z * s4[ps].w;
+              v = o;
+            }
+            const int b = row / a.T, t = row % a.T;
+            bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)b * a.H + h) * a.T + t) * a.hdp + d;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+          }
+          continue;
+        }
+
 #pragma unroll
         for (int ps = 0; ps < LPR; ++ps) {
-          const int rr = ps * RPP + lane / LPR;
-          const int cc = (lane % LPR) * 4;
-          const int row = m0 + q * 32 + rr;
-          const int col = n0 + c0 + cc;
-          if (row >= a.M || col >= a.N) continue;
-          float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + cc);
-          if (EPI != TC_EPI_QKV && a.bias) {
-            float4 bb = *reinterpret_cast<const float4*>(a.bias + col);
-            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-          }
+          const int rr = ps * RPP + prow;
+          const int row = wrow0 + rr;
+          if (row >= a.M || !col_ok) continue;
+          float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + pcc);
+          v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
           if (EPI == TC_EPI_BIAS_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = v;
           } else if (EPI == TC_EPI_BIAS_BF16 || EPI == TC_EPI_GELU_BF16) {
@@ -316,35 +430,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
             *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo + col) = pk;
-          } else if (EPI == TC_EPI_GATED_RESIDUAL) {
-            // x = x + gate.unsqueeze(1) * f(...)   lightningdit.py:248-249
-            const int b = row / a.T;
-            float4 g = *reinterpret_cast<const float4*>(a.mod + (size_t)b * a.mod_ld + a.gate_off + col);
-            float4* xp = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col);
-            float4 x = *xp;
-            x.x = fmaf(g.x, v.x, x.x); x.y = fmaf(g.y, v.y, x.y); x.z = fmaf(g.z, v.z, x.z); x.w = fmaf(g.w, v.w, x.w);
-            *xp = x;
           } else if (EPI == TC_EPI_SWIGLU) {
             // rows of w12 are interleaved at pack time: column 2j = x1[j] (gated), 2j+1 = x2[j]; swiglu_ffn.py:33-35
             uint32_t pk = pack_bf16(silu_fast(v.x) * v.y, silu_fast(v.z) * v.w);
             *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo + (col >> 1)) = pk;
-          } else if (EPI == TC_EPI_QKV) {
-            const int D = a.H * a.hd;
-            const int which = col / D, rem = col - which * D, h = rem / a.hd, d = rem % a.hd;
-            const int b = row / a.T, t = row % a.T;
-            if (a.cos) {
-              // t*cos + rotate_half(t)*sin with (a,b) -> (-b,a) on adjacent pairs; pos_embed.py:38-42,135
-              float4 c4 = *reinterpret_cast<const float4*>(a.cos + (size_t)t * a.hd + d);
-              float4 s4 = *reinterpret_cast<const float4*>(a.sin + (size_t)t * a.hd + d);
-              float4 o;
-              o.x = v.x * c4.x - v.y * s4.x;
-              o.y = v.y * c4.y + v.x * s4.y;
-              o.z = v.z * c4.z - v.w * s4.z;
-              o.w = v.w * c4.w + v.z * s4.w;
-              v = o;
-            }
-            bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)b * a.H + h) * a.T + t) * a.hdp + d;
-            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
           }
         }
       }
@@ -411,7 +500,7 @@ int gemm_tc_pick_bn(const TcGemmArgs& a) {
 template <int EPI, int CW>
 static void launch_inst(const TcGemmArgs& a, int BN, cudaStream_t s) {
   const int stage_bytes = TC_A_BYTES + BN * 128;
-  const int fixed = 4 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024;
+  const int fixed = 8 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024;
   int nstages = (227 * 1024 - fixed) / stage_bytes;
   if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
   VV_CHECK(nstages >= 2, "gemm_tc: tile too large for shared memory");

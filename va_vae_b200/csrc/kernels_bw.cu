@@ -169,7 +169,18 @@ __global__ void __launch_bounds__(256) k_norm_modulate(NormModArgs a) {
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo)[c] = pk;
+        bf16* orow = reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo;
+        reinterpret_cast<uint2*>(orow)[c] = pk;
+        if (a.split3) {
+          // residual of the bf16 rounding, itself rounded to bf16: x = hi + lo + O(2^-17 |x|)
+          __nv_bfloat162 r0 = __floats2bfloat162_rn(o.x - __low2float(lo), o.y - __high2float(lo));
+          __nv_bfloat162 r1 = __floats2bfloat162_rn(o.z - __low2float(hi), o.w - __high2float(hi));
+          uint2 pr;
+          pr.x = *reinterpret_cast<uint32_t*>(&r0);
+          pr.y = *reinterpret_cast<uint32_t*>(&r1);
+          reinterpret_cast<uint2*>(orow + a.D)[c] = pr;
+          reinterpret_cast<uint2*>(orow + 2 * a.D)[c] = pk;
+        }
       } else {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo)[c] = o;
       }

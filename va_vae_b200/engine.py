@@ -23,7 +23,7 @@ EXPORTS = [
     "vavae_abi_version", "vavae_last_error", "vavae_create", "vavae_destroy", "vavae_load_weight", "vavae_finalize",
     "vavae_forward", "vavae_forward_with_cfg", "vavae_sample_ode", "vavae_sample_ode_host", "vavae_launch_count",
     "vavae_device_bytes", "vavae_test_gemm_bf16", "vavae_test_attention_bf16", "vavae_time_kernel",
-    "vavae_set_attention_variant",
+    "vavae_set_attention_variant", "vavae_profile_begin", "vavae_profile_end",
 ]
 
 
@@ -70,6 +70,9 @@ def load_library() -> ctypes.CDLL:
     lib.vavae_time_kernel.argtypes = [c_void, ctypes.c_char_p, c_int, c_int, ctypes.POINTER(c_float),
                                       ctypes.POINTER(ctypes.c_double), c_void]
     lib.vavae_set_attention_variant.argtypes = [c_int]
+    lib.vavae_profile_begin.argtypes = [c_void, ctypes.c_char_p]
+    lib.vavae_profile_end.argtypes = [c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_double)]
     if lib.vavae_abi_version() != ABI_VERSION:
         raise RuntimeError("libvavae_b200.so ABI version mismatch; rebuild with python -m va_vae_b200.build --force")
     _lib = lib
@@ -216,6 +219,15 @@ class Engine:
             _check(self._lib.vavae_time_kernel(self._h, kernel.encode(), rows, iters, ctypes.byref(ms),
                                                ctypes.byref(work), ctypes.c_void_p(_stream(self.device))))
         return ms.value, work.value
+
+    def profile_begin(self, kernel):
+        _check(self._lib.vavae_profile_begin(self._h, kernel.encode() if kernel else None))
+
+    def profile_end(self):
+        """(summed ms, launches, summed algorithmic work) of the kernel class selected by profile_begin."""
+        ms, n, work = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+        _check(self._lib.vavae_profile_end(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(work)))
+        return ms.value, n.value, work.value
 
     @property
     def launch_count(self) -> int:
