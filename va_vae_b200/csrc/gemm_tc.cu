@@ -301,22 +301,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             continue;
           }
-          // q / k (and fast-path v): bias (+ optional qk-norm) in the thread == row domain
+          // q / k with qk-norm: bias + normalisation in the thread == row domain (needs whole-head statistics).
+          // Without qk-norm (production flags) the bias is added later in the coalesced row-wise pass.
           const float* nw = which == 0 ? a.qn_w : (which == 1 ? a.kn_w : nullptr);
           const float* nb = which == 0 ? a.qn_b : (which == 1 ? a.kn_b : nullptr);
+          if (nw) {
+            float bj[CW];
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const int col = colc + j;
-            float v = __uint_as_float(r[j]) + (col < a.N ? a.bias[col] : 0.f);
-            if (nw) {
+            for (int j = 0; j < CW; ++j) bj[j] = a.bias[colc + j];  // independent loads, issued back to back
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              const int col = colc + j;
+              float v = __uint_as_float(r[j]) + bj[j];
               const int rem = col - which * D, h = rem / a.hd, d = rem % a.hd;
               if (h != qk_head) {
                 qk_head = h;
                 qk_head_stats(tbase, which * D + h * a.hd - n0, n0, a.hd, a.bias, a.qk_rms, qk_mean, qk_rstd);
               }
               v = (v - qk_mean) * qk_rstd * nw[d] + (nb ? nb[d] : 0.f);
+              r[j] = __float_as_uint(v);
             }
-            r[j] = __float_as_uint(v);
           }
         }
 
@@ -341,9 +345,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int col = n0 + c0 + j;
             if (col < a.N && wrow0 + tg * 8 < a.M) {
               const int rem = col - 2 * D, h = rem / a.hd, d = rem % a.hd;
+              const float bv = a.bias[col];
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = st[(tg * 8 + e) * (CW + 4) + j];
+              for (int e = 0; e < 8; ++e) f[e] = st[(tg * 8 + e) * (CW + 4) + j] + bv;
               uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
               *reinterpret_cast<uint4*>(a.vt + (((size_t)b * a.H + h) * a.hdv + d) * a.T + t0 + tg * 8) = pk;
             }
@@ -354,7 +359,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int col = n0 + c0 + pcc;  // this lane's 4 columns in every pass
         const bool col_ok = col < a.N;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EPI != TC_EPI_QKV && a.bias && col_ok) bb = *reinterpret_cast<const float4*>(a.bias + col);
+        if (a.bias && col_ok && (EPI != TC_EPI_QKV || !a.qn_w)) bb = *reinterpret_cast<const float4*>(a.bias + col);
 
         if (EPI == TC_EPI_GATED_RESIDUAL) {
           // x = x + gate.unsqueeze(1) * f(...)   lightningdit.py:248-249 ; x was prefetched one chunk ahead
@@ -400,6 +405,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int row = wrow0 + rr;
             if (row >= a.M || !col_ok) continue;
             float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + pcc);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;  // zero when qk-norm already consumed the bias
             if (a.cos) {
               float4 o;
               o.x = v.x * c4[ps].x - v.y * s4[ps].x;
