@@ -124,12 +124,11 @@ int vavae_profile_end(vavae_engine_t* e, double* total_ms, int64_t* launches, do
 int vavae_test_gemm_bf16(const void* A, const void* W, const float* bias, float* C, int M, int N, int K,
                          void* stream);
 /* O[B*T, H*hd] (bf16) = softmax(q k^T / sqrt(hd)) v on the tcgen05 attention kernel.
- * q, k: (B,H,T,hd_pad) bf16; vt: (B,H,hd_v_pad,T) bf16 (see DESIGN.md "attention layouts"). */
+ * q, k: (B,H,T,hdp) bf16, hdp = head_dim rounded up to 16, padding zero; vt: (B,H,hdv,T) bf16 with
+ * hdv = (head_dim + 1) rounded up to 16, rows [0,hd) = v^T, row hd = ones, remaining rows zero
+ * (see DESIGN.md "attention layouts"). */
 int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int T, int hd,
                               void* stream);
-/* Selects where the attention kernel keeps the bf16 probabilities P: 1 = tensor memory (TS MMA, default),
- * 0 = 128B-swizzled shared memory (SS MMA).  Process-wide. */
-int vavae_set_attention_variant(int p_in_tmem);
 /* Per-kernel timing: runs the named kernel of the engine's own layer 0 `iters` times on the given
  * number of model rows with CUDA events on `stream`; returns mean milliseconds per launch in *ms. */
 int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work,

@@ -37,28 +37,31 @@ def test_tcgen05_gemm_matches_fp32_matmul(M, N, K):
 def _attn_inputs(B, H, T, hd, dev, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     hdp = (hd + 15) // 16 * 16
+    hdv = (hd + 1 + 15) // 16 * 16      # + the ones row that yields the softmax row sums
     q = torch.randn(B, H, T, hd, generator=g).to(dev).bfloat16()
     k = torch.randn(B, H, T, hd, generator=g).to(dev).bfloat16()
     v = torch.randn(B, H, T, hd, generator=g).to(dev).bfloat16()
     qp = torch.zeros(B, H, T, hdp, device=dev, dtype=torch.bfloat16)
     kp = torch.zeros_like(qp)
-    vt = torch.zeros(B, H, hdp, T, device=dev, dtype=torch.bfloat16)
+    vt = torch.zeros(B, H, hdv, T, device=dev, dtype=torch.bfloat16)
     qp[..., :hd], kp[..., :hd] = q, k
     vt[:, :, :hd, :] = v.transpose(2, 3)
+    vt[:, :, hd, :] = 1.0
     return q, k, v, qp.contiguous(), kp.contiguous(), vt.contiguous()
 
 
-@pytest.mark.parametrize("p_in_tmem", [True, False])
-@pytest.mark.parametrize("B,H,T,hd", [(2, 2, 256, 64), (2, 3, 256, 72), (3, 2, 16, 32), (2, 2, 64, 64),
-                                      (1, 2, 1024, 72), (2, 2, 1024, 64), (4, 16, 256, 72)])
-def test_tcgen05_attention_matches_fp32_softmax(B, H, T, hd, p_in_tmem):
+@pytest.mark.parametrize("B,H,T,hd", [(2, 2, 256, 64), (2, 3, 256, 72), (3, 2, 16, 32), (2, 2, 64, 64), (2, 2, 24, 16),
+                                      (1, 2, 1024, 72), (2, 2, 1024, 64), (4, 16, 256, 72), (64, 12, 256, 64),
+                                      (3, 5, 640, 96)])
+def test_tcgen05_attention_matches_fp32_softmax(B, H, T, hd):
     from va_vae_b200 import engine as E
     dev = _dev()
     q, k, v, qp, kp, vt = _attn_inputs(B, H, T, hd, dev, seed=T + hd)
-    out = E.test_attention_bf16(qp, kp, vt, hd, p_in_tmem=p_in_tmem)
+    out = E.test_attention_bf16(qp, kp, vt, hd)
     torch.cuda.synchronize()
     att = torch.softmax((q.float() @ k.float().transpose(-1, -2)) / math.sqrt(hd), dim=-1)
     ref = (att @ v.float()).transpose(1, 2).reshape(B * T, H * hd)
     err = rel_l2(out.float(), ref)
-    # P and the output are rounded to bf16 (2^-9 relative): 1e-2 bar of BASELINE.json with >2x margin
-    assert err < 4e-3, f"attention B{B} H{H} T{T} hd{hd} p_in_tmem={p_in_tmem}: rel-L2 {err:.3e}"
+    # exp2 argument, P and the output are rounded to bf16 (2^-9 relative): 1e-2 bar of BASELINE.json with margin
+    print(f"attention B{B} H{H} T{T} hd{hd}: rel-L2 {err:.3e}")
+    assert err < 6e-3, f"attention B{B} H{H} T{T} hd{hd}: rel-L2 {err:.3e}"

@@ -1,36 +1,33 @@
 // tcgen05 flash attention for sm_100a:  O = softmax(Q K^T / sqrt(hd)) V   (lightningdit.py:77-88)
-// One CTA per (batch*head, 128-query tile), keys processed in blocks of 256 with an online softmax.
-//   S = Q K^T   : tcgen05.mma  M=128, N=keys (<=256), K=hd padded to 16        -> TMEM columns [0,256)
-//   softmax     : 128 threads, thread == query row, S read with tcgen05.ld, exp2 on fp32
-//   P           : bf16 probabilities written back into TMEM (packed two per column, aliasing S columns
-//                 [0,128)) and consumed as the TMEM A-operand of the second MMA
-//   O = P V     : tcgen05.mma  M=128, N=hd padded to 16, K=keys                 -> TMEM columns [128,256)
-// Layouts (all K-major, 128B-swizzled TMA tiles): q,k (B,H,T,hdp) ; v stored transposed (B,H,hdv,T) by the
-// QKV GEMM epilogue so that P V needs no MN-major operand.  256 TMEM columns and <=113 KB of shared memory
-// per CTA so two CTAs share an SM and overlap each other's TMA / MMA / softmax phases.
+//
+// Persistent kernel, two CTAs per SM; a work item is one (batch*head, 128-query tile) and keys are processed in
+// blocks of 256 with an online softmax.  Per block ("step"):
+//   S = Q K^T   : tcgen05.mma  M=128, N=keys (<=256), K=hd padded to 16         -> TMEM columns [0,256)
+//   softmax     : 128 threads, thread == query row; S read with tcgen05.ld; p = ex2.approx.bf16x2 on the packed
+//                 bf16 pair (one MUFU op per two probabilities), written straight back into TMEM
+//   P           : bf16, two per 32-bit TMEM column, aliasing S columns [0,128); TMEM A-operand of the second MMA
+//   O = P V     : tcgen05.mma  M=128, N=hdv, K=keys                              -> TMEM columns [128,128+hdv)
+//   row sums    : V^T carries a row of ones at index hd, so column hd of O *is* sum_j P_ij (exactly the bf16
+//                 probabilities the MMA consumed) - no summation instructions in the softmax loop.
+// TMA loads are software-pipelined across steps with single buffers: Q/K of step s+1 are requested as soon as
+// the S MMA of step s retires, V of step s+1 as soon as the P V MMA of step s retires, so their latency hides
+// behind the softmax of step s.  The second CTA on the SM fills the tensor/MUFU pipes meanwhile.
+//
+// Layouts (all K-major TMA tiles, 128-byte swizzle): q,k (B,H,T,hdp); v transposed (B,H,hdv,T), written by the
+// QKV GEMM epilogue.  A 16-column tail of hdp (head_dim 72 -> 80) is loaded as a compact 32-byte-swizzled tile.
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
 namespace vv {
 
-constexpr int AT_BQ = 128;   // queries per CTA
-constexpr int AT_BKV = 256;  // keys per block
+constexpr int AT_BQ = 128;   // queries per work item
+constexpr int AT_BKV = 256;  // keys per step
 constexpr int AT_THREADS = 160;
 
 struct AtBars {
-  uint64_t q_full, kv_full, s_full, p_full, o_full, o_empty;
+  uint64_t qk_full, v_full, s_full, p_full, o_full, o_empty, qk_empty, v_empty;
   uint32_t tmem_base;
 };
-
-__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T  (A operand from tensor memory)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -44,43 +41,80 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// P_IN_TMEM = true : P goes to TMEM (TS MMA), 2 CTAs / SM.
-// P_IN_TMEM = false: P goes to 128B-swizzled shared memory (SS MMA) - conservative variant kept for bring-up.
-template <bool P_IN_TMEM, bool MULTI>
-__global__ void __launch_bounds__(AT_THREADS, (P_IN_TMEM && !MULTI) ? 2 : 1)
+// K-major operand tile whose rows are 32 bytes (16 bf16) with the 32-byte swizzle (CU_TENSOR_MAP_SWIZZLE_32B):
+// 8-row groups are 256 bytes apart; layout type 6.
+__device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+// two fp32 -> packed bf16x2 (lo = first), then 2^x on both halves with one MUFU instruction
+__device__ __forceinline__ uint32_t ex2_bf16x2(float x0, float x1) {
+  uint32_t packed, out;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(x1), "f"(x0));
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(out) : "r"(packed));
+  return out;
+}
+
+struct AtGeom {
+  int n_full;     // number of full 64-column atoms of Q/K
+  int tail16;     // 1: a compact 16-column tail tile follows the full atoms
+  int q_bytes, k_bytes, v_atom, v_bytes;
+};
+__host__ __device__ inline AtGeom at_geom(int hdp, int hdv) {
+  AtGeom g;
+  g.tail16 = (hdp % 64 == 16) ? 1 : 0;
+  g.n_full = g.tail16 ? hdp / 64 : (hdp + 63) / 64;
+  g.q_bytes = g.n_full * AT_BQ * 128 + g.tail16 * AT_BQ * 32;
+  g.k_bytes = g.n_full * AT_BKV * 128 + g.tail16 * AT_BKV * 32;
+  g.v_atom = hdv * 128;
+  g.v_bytes = 4 * g.v_atom;
+  return g;
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(AT_THREADS, 2)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const TcAttnArgs a) {
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQt,
+               const __grid_constant__ CUtensorMap tmKt, const TcAttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int nka = (a.hdp + 63) / 64;               // 64-column atoms along head_dim for Q / K
-  const int q_bytes = nka * AT_BQ * 128;
-  const int k_bytes = nka * AT_BKV * 128;
-  const int v_atom = a.hdv * 128;                  // one 64-key atom of V^T
-  const int v_bytes = 4 * v_atom;
+  const AtGeom g = at_geom(a.hdp, a.hdv);
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + q_bytes;
-  uint8_t* sV = sK + k_bytes;
-  uint8_t* sP = sV + v_bytes;                      // only used when !P_IN_TMEM (4 atoms x 16 KiB)
-  AtBars* bars = reinterpret_cast<AtBars*>(sP + (P_IN_TMEM ? 0 : 4 * AT_BQ * 128));
+  uint8_t* sK = sQ + ((g.q_bytes + 1023) & ~1023);
+  uint8_t* sV = sK + ((g.k_bytes + 1023) & ~1023);
+  AtBars* bars = reinterpret_cast<AtBars*>(sV + g.v_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.y;
-  const int q0 = blockIdx.x * AT_BQ;
+  const int nq = (a.T + AT_BQ - 1) / AT_BQ;
   const int nblk = (a.T + AT_BKV - 1) / AT_BKV;
-  constexpr uint32_t TMEM_COLS = P_IN_TMEM ? 256 : 512;
-  constexpr uint32_t O_COL = P_IN_TMEM ? 128 : 256;
+  const int n_items = a.B * a.H * nq;
+  constexpr uint32_t TMEM_COLS = 256;
+  constexpr uint32_t O_COL = 128;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
-    ptx::mbar_init(&bars->q_full, 1);
-    ptx::mbar_init(&bars->kv_full, 1);
+    ptx::mbar_init(&bars->qk_full, 1);
+    ptx::mbar_init(&bars->v_full, 1);
     ptx::mbar_init(&bars->s_full, 1);
     ptx::mbar_init(&bars->p_full, 128);
     ptx::mbar_init(&bars->o_full, 1);
     ptx::mbar_init(&bars->o_empty, 128);
+    ptx::mbar_init(&bars->qk_empty, 1);
+    ptx::mbar_init(&bars->v_empty, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 4) {
@@ -95,53 +129,82 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 4) {
     // ------------------------------------------------------------- control thread: TMA + MMA issue
     if (lane == 0) {
-      ptx::mbar_expect_tx(&bars->q_full, (uint32_t)q_bytes);
-      for (int ka = 0; ka < nka; ++ka)
-        ptx::tma_load_3d(sQ + ka * AT_BQ * 128, &tmQ, &bars->q_full, ka * 64, q0, bh);
-      for (int blk = 0; blk < nblk; ++blk) {
-        const uint32_t ph = blk & 1;
-        const int kv0 = blk * AT_BKV;
-        const int kvlen = min(AT_BKV, a.T - kv0);
-        const int n_s = ((kvlen + 15) / 16) * 16;  // MMA N for S / K extent for P V
-        if (blk > 0) ptx::mbar_wait(&bars->o_full, ph ^ 1);  // previous P V done: K / V tiles reusable
-        ptx::mbar_expect_tx(&bars->kv_full, (uint32_t)(k_bytes + v_bytes));
-        for (int ka = 0; ka < nka; ++ka)
-          ptx::tma_load_3d(sK + ka * AT_BKV * 128, &tmK, &bars->kv_full, ka * 64, kv0, bh);
-        for (int kk = 0; kk < 4; ++kk)
-          ptx::tma_load_3d(sV + kk * v_atom, &tmV, &bars->kv_full, kv0 + kk * 64, 0, bh);
-        if (blk == 0) ptx::mbar_wait(&bars->q_full, 0);
-        ptx::mbar_wait(&bars->kv_full, ph);
-        if (blk > 0) ptx::mbar_wait(&bars->o_empty, ph ^ 1);  // softmax threads have drained the previous O block
-        ptx::tc_fence_after();
-        // S = Q K^T
-        {
-          const uint32_t idesc = ptx::make_idesc_bf16(AT_BQ, n_s);
-          const int ksteps = a.hdp / 16;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const int atom = ks >> 2, kin = ks & 3;
-            const uint64_t ad = ptx::make_desc_k_sw128(ptx::smem_u32(sQ + atom * AT_BQ * 128)) + (uint64_t)(kin * 2);
-            const uint64_t bd = ptx::make_desc_k_sw128(ptx::smem_u32(sK + atom * AT_BKV * 128)) + (uint64_t)(kin * 2);
-            ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
-          }
-          ptx::umma_commit(&bars->s_full);
+      // step = (item, blk) flattened; loads for a step: K (+Q on the first block of an item), and V
+      auto load_qk = [&](int item, int blk) {
+        const int bh = item / nq, q0 = (item % nq) * AT_BQ, kv0 = blk * AT_BKV;
+        ptx::mbar_expect_tx(&bars->qk_full, (uint32_t)(g.k_bytes + (blk == 0 ? g.q_bytes : 0)));
+        for (int ka = 0; ka < g.n_full; ++ka) {
+          ptx::tma_load_3d(sK + ka * AT_BKV * 128, &tmK, &bars->qk_full, ka * 64, kv0, bh);
+          if (blk == 0) ptx::tma_load_3d(sQ + ka * AT_BQ * 128, &tmQ, &bars->qk_full, ka * 64, q0, bh);
         }
-        // O_blk = P V
-        ptx::mbar_wait(&bars->p_full, ph);
-        ptx::tc_fence_after();
-        {
-          const uint32_t idesc = ptx::make_idesc_bf16(AT_BQ, a.hdv);
-          const int ksteps = n_s / 16;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const int atom = ks >> 2, kin = ks & 3;
-            const uint64_t bd = ptx::make_desc_k_sw128(ptx::smem_u32(sV + atom * v_atom)) + (uint64_t)(kin * 2);
-            if (P_IN_TMEM) {
-              umma_bf16_ts(tmem_base + O_COL, tmem_base + (uint32_t)(ks * 8), bd, idesc, (uint32_t)(ks != 0));
-            } else {
-              const uint64_t ad = ptx::make_desc_k_sw128(ptx::smem_u32(sP + atom * AT_BQ * 128)) + (uint64_t)(kin * 2);
-              ptx::umma_bf16_ss(tmem_base + O_COL, ad, bd, idesc, (uint32_t)(ks != 0));
+        if (g.tail16) {
+          ptx::tma_load_3d(sK + g.n_full * AT_BKV * 128, &tmKt, &bars->qk_full, g.n_full * 64, kv0, bh);
+          if (blk == 0) ptx::tma_load_3d(sQ + g.n_full * AT_BQ * 128, &tmQt, &bars->qk_full, g.n_full * 64, q0, bh);
+        }
+      };
+      auto load_v = [&](int item, int blk) {
+        const int bh = item / nq, kv0 = blk * AT_BKV;
+        ptx::mbar_expect_tx(&bars->v_full, (uint32_t)g.v_bytes);
+        for (int kk = 0; kk < 4; ++kk) ptx::tma_load_3d(sV + kk * g.v_atom, &tmV, &bars->v_full, kv0 + kk * 64, 0, bh);
+      };
+      uint32_t step = 0;
+      if ((int)blockIdx.x < n_items) {
+        load_qk(blockIdx.x, 0);
+        load_v(blockIdx.x, 0);
+      }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        for (int blk = 0; blk < nblk; ++blk, ++step) {
+          const uint32_t ph = step & 1;
+          const int kvlen = min(AT_BKV, a.T - blk * AT_BKV);
+          const int n_s = ((kvlen + 15) / 16) * 16;  // MMA N for S / K extent of P V
+          // next step (for prefetch)
+          int nitem = item, nblkk = blk + 1;
+          if (nblkk == nblk) { nitem = item + gridDim.x; nblkk = 0; }
+          const bool has_next = nitem < n_items;
+
+          ptx::mbar_wait(&bars->qk_full, ph);
+          if (step > 0) ptx::mbar_wait(&bars->o_empty, ph ^ 1);  // softmax threads drained the previous O / P
+          ptx::tc_fence_after();
+          {  // S = Q K^T
+            const uint32_t idesc = ptx::make_idesc_bf16(AT_BQ, n_s);
+            int ks = 0;
+            for (int ka = 0; ka < g.n_full; ++ka) {
+              const int kmax = min(4, (a.hdp - ka * 64) / 16);
+              for (int kin = 0; kin < kmax; ++kin, ++ks) {
+                const uint64_t ad = ptx::make_desc_k_sw128(ptx::smem_u32(sQ + ka * AT_BQ * 128)) + (uint64_t)(kin * 2);
+                const uint64_t bd = ptx::make_desc_k_sw128(ptx::smem_u32(sK + ka * AT_BKV * 128)) + (uint64_t)(kin * 2);
+                ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
+              }
             }
+            if (g.tail16) {
+              const uint64_t ad = make_desc_k_sw32(ptx::smem_u32(sQ + g.n_full * AT_BQ * 128));
+              const uint64_t bd = make_desc_k_sw32(ptx::smem_u32(sK + g.n_full * AT_BKV * 128));
+              ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
+            }
+            ptx::umma_commit(&bars->s_full);
+            ptx::umma_commit(&bars->qk_empty);
           }
-          ptx::umma_commit(&bars->o_full);
+          // Q/K tiles are free once S retires: request the next step's Q/K now (hidden behind this softmax)
+          ptx::mbar_wait(&bars->qk_empty, ph);
+          if (has_next) load_qk(nitem, nblkk);
+
+          // O_blk = P V
+          ptx::mbar_wait(&bars->v_full, ph);
+          ptx::mbar_wait(&bars->p_full, ph);
+          ptx::tc_fence_after();
+          {
+            const uint32_t idesc = ptx::make_idesc_bf16(AT_BQ, a.hdv);
+            const int ksteps = n_s / 16;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const int atom = ks >> 2, kin = ks & 3;
+              const uint64_t bd = ptx::make_desc_k_sw128(ptx::smem_u32(sV + atom * g.v_atom)) + (uint64_t)(kin * 2);
+              umma_bf16_ts(tmem_base + O_COL, tmem_base + (uint32_t)(ks * 8), bd, idesc, (uint32_t)(ks != 0));
+            }
+            ptx::umma_commit(&bars->o_full);
+            ptx::umma_commit(&bars->v_empty);
+          }
+          ptx::mbar_wait(&bars->v_empty, ph);
+          if (has_next) load_v(nitem, nblkk);
         }
       }
     }
@@ -150,127 +213,158 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int row = warp * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float sl2 = rsqrtf((float)a.hd) * 1.4426950408889634f;  // scale * log2(e)
-    float m_run = -INFINITY, l_run = 0.f;
-    constexpr bool multi = MULTI;
-    float oacc[MULTI ? 128 : 1];
+    const int ncol_o = a.hd + 1;                                   // head_dim columns + the row-sum column
+    uint32_t step = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int bh = item / nq, q0 = (item % nq) * AT_BQ;
+      float m_run = -INFINITY;
+      float oacc[MULTI ? 128 : 1];
 #pragma unroll
-    for (int i = 0; i < (MULTI ? 128 : 1); ++i) oacc[i] = 0.f;
-    for (int blk = 0; blk < nblk; ++blk) {
-      const uint32_t ph = blk & 1;
-      const int kvlen = min(AT_BKV, a.T - blk * AT_BKV);
-      const int n_s = ((kvlen + 15) / 16) * 16;
-      ptx::mbar_wait(&bars->s_full, ph);
-      ptx::tc_fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
-      for (int c0 = 0; c0 < n_s; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(trow + c0, r);
-        ptx::tmem_ld_wait();
+      for (int i = 0; i < (MULTI ? 128 : 1); ++i) oacc[i] = 0.f;
+
+      for (int blk = 0; blk < nblk; ++blk, ++step) {
+        const uint32_t ph = step & 1;
+        const int kvlen = min(AT_BKV, a.T - blk * AT_BKV);
+        const int n_s = ((kvlen + 15) / 16) * 16;
+        const bool ragged = (kvlen & 15) != 0;  // only the last 16-column group can hold invalid keys
+        ptx::mbar_wait(&bars->s_full, ph);
+        ptx::tc_fence_after();
+        // pass 1: row maximum
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < n_s; c0 += 32) {
+          uint32_t r[32];
+          if (c0 + 32 <= n_s) {
+            ptx::tmem_ld_x32(trow + c0, r);
+          } else {
+            ptx::tmem_ld_x16(trow + c0, r);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < kvlen) mx = fmaxf(mx, __uint_as_float(r[j]));
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * sl2);  // 0 on the first block (m_run = -inf)
-      const float moff = m_new * sl2;
-      // pass 2: p = exp2(s*scale*log2e - m), row sum, bf16 P
-      float rs = 0.f;
-      for (int c0 = 0; c0 < n_s; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(trow + c0, r);
-        ptx::tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float p0 = (c0 + j < kvlen) ? exp2f(fmaf(__uint_as_float(r[j]), sl2, -moff)) : 0.f;
-          float p1 = (c0 + j + 1 < kvlen) ? exp2f(fmaf(__uint_as_float(r[j + 1]), sl2, -moff)) : 0.f;
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-          // the row sum uses the rounded probabilities so numerator and denominator agree
-          rs += __low2float(b2) + __high2float(b2);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        if (P_IN_TMEM) {
-          // 16 keys -> 8 packed columns; written 16 keys behind the read front so S is never clobbered early
-          // (tcgen05.st x16 needs 16 registers: stage two chunks)
-          // simple form: write 8 columns with an x8 store
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(
-                           trow + (uint32_t)(c0 >> 1)),
-                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                       : "memory");
-        } else {
-          // K-major SW128 tile: atom = 64 keys, row = 128 B, 16-byte chunk index XOR (row & 7)
-          const int atom = c0 >> 6, ch = (c0 & 63) >> 3;
-          uint8_t* base = sP + atom * AT_BQ * 128 + row * 128;
-          *reinterpret_cast<uint4*>(base + (((ch) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(base + (((ch + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-      }
-      if (P_IN_TMEM) tmem_st_wait();
-      else ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bars->p_full);
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
-      // O
-      ptx::mbar_wait(&bars->o_full, ph);
-      ptx::tc_fence_after();
-      if (multi) {
-        for (int c0 = 0; c0 < a.hdv; c0 += 16) {
-          uint32_t r[16];
-          ptx::tmem_ld_x16(trow + O_COL + c0, r);
+            for (int j = 16; j < 32; ++j) r[j] = 0xff800000u;  // -inf
+          }
           ptx::tmem_ld_wait();
-          // oacc is only ever indexed with compile-time constants (fully unrolled, guarded by c0)
+          if (ragged && c0 + 32 >= kvlen) {
 #pragma unroll
-          for (int cc = 0; cc < (MULTI ? 8 : 0); ++cc) {
-            if (c0 == cc * 16) {
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j >= kvlen) r[j] = 0xff800000u;
+          }
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-              for (int j = 0; j < 16; ++j) oacc[cc * 16 + j] = oacc[cc * 16 + j] * alpha + __uint_as_float(r[j]);
+          for (int j = 0; j < 32; j += 4) {
+            m4[0] = fmaxf(m4[0], __uint_as_float(r[j]));
+            m4[1] = fmaxf(m4[1], __uint_as_float(r[j + 1]));
+            m4[2] = fmaxf(m4[2], __uint_as_float(r[j + 2]));
+            m4[3] = fmaxf(m4[3], __uint_as_float(r[j + 3]));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = exp2f((m_run - m_new) * sl2);  // 0 on the first block (m_run = -inf)
+        const float moff = m_new * sl2;
+        m_run = m_new;
+        // pass 2: p = 2^(s*scale*log2e - m) as packed bf16 pairs, written back to TMEM (16 keys -> 8 columns;
+        // the write front at c0/2 never passes the read front at c0, so S is not clobbered before it is read)
+        for (int c0 = 0; c0 < n_s; c0 += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld_x16(trow + c0, r);
+          ptx::tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float x0 = fmaf(__uint_as_float(r[j]), sl2, -moff);
+            float x1 = fmaf(__uint_as_float(r[j + 1]), sl2, -moff);
+            if (ragged) {
+              if (c0 + j >= kvlen) x0 = -INFINITY;
+              if (c0 + j + 1 >= kvlen) x1 = -INFINITY;
+            }
+            pk[j >> 1] = ex2_bf16x2(x0, x1);
+          }
+          tmem_st_x8(trow + (uint32_t)(c0 >> 1), pk);
+        }
+        tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars->p_full);
+
+        // O block (and, in column hd, the row sum of the probabilities the MMA consumed)
+        ptx::mbar_wait(&bars->o_full, ph);
+        ptx::tc_fence_after();
+        const bool last = blk == nblk - 1;
+        if (!MULTI) {
+          // single block: normalise and store straight from TMEM
+          uint32_t rl[16];
+          ptx::tmem_ld_x16(trow + O_COL + (uint32_t)((a.hd >> 4) << 4), rl);  // the 16-column group holding column hd
+          ptx::tmem_ld_wait();
+          float l = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j == (a.hd & 15)) l = __uint_as_float(rl[j]);
+          const float inv = 1.0f / l;
+          const int b = bh / a.H, h = bh % a.H;
+          const bool valid = (q0 + row) < a.T;
+          bf16* orow = a.out + ((size_t)b * a.T + q0 + row) * ((size_t)a.H * a.hd) + (size_t)h * a.hd;
+          for (int c0 = 0; c0 < a.hd; c0 += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld_x16(trow + O_COL + c0, r);
+            ptx::tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int j8 = 0; j8 < 2; ++j8) {
+                if (c0 + j8 * 8 < a.hd) {  // hd % 8 == 0
+                  uint4 pk;
+                  __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 0]) * inv, __uint_as_float(r[j8 * 8 + 1]) * inv);
+                  __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 2]) * inv, __uint_as_float(r[j8 * 8 + 3]) * inv);
+                  __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 4]) * inv, __uint_as_float(r[j8 * 8 + 5]) * inv);
+                  __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 6]) * inv, __uint_as_float(r[j8 * 8 + 7]) * inv);
+                  pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                  *reinterpret_cast<uint4*>(orow + c0 + j8 * 8) = pk;
+                }
+              }
             }
           }
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars->o_empty);
-      }
-    }
-    // ---- write O / l   (token-major [B*T, H*hd], head h occupies columns h*hd..)
-    const int b = bh / a.H, h = bh % a.H;
-    const float inv = 1.0f / l_run;
-    const bool valid = (q0 + row) < a.T;
-    bf16* orow = a.out + ((size_t)b * a.T + q0 + row) * ((size_t)a.H * a.hd) + (size_t)h * a.hd;
-    for (int c0 = 0; c0 < a.hdv; c0 += 16) {
-      uint32_t r[16];
-      if (!multi) {
-        ptx::tmem_ld_x16(trow + O_COL + c0, r);
-        ptx::tmem_ld_wait();
-      }
-      float v[16];
-      if (MULTI) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars->o_empty);
+        } else {
+          // online softmax: rescale the running O (and running row sum in column hd) and add this block
+          for (int c0 = 0; c0 < ncol_o; c0 += 16) {
+            uint32_t r[16];
+            ptx::tmem_ld_x16(trow + O_COL + c0, r);
+            ptx::tmem_ld_wait();
+            // oacc is only ever indexed with compile-time constants (fully unrolled, guarded by c0)
 #pragma unroll
-        for (int cc = 0; cc < (MULTI ? 8 : 0); ++cc) {
-          if (c0 == cc * 16) {
+            for (int cc = 0; cc < (MULTI ? 8 : 0); ++cc) {
+              if (c0 == cc * 16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = oacc[cc * 16 + j] * inv;
+                for (int j = 0; j < 16; ++j) oacc[cc * 16 + j] = oacc[cc * 16 + j] * alpha + __uint_as_float(r[j]);
+              }
+            }
           }
-        }
-      } else {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars->o_empty);
+          if (last) {
+            float l = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * inv;
-      }
-      if (valid) {
+            for (int i = 0; i < (MULTI ? 128 : 0); ++i)
+              if (i == a.hd) l = oacc[i];
+            const float inv = 1.0f / l;
+            const int b = bh / a.H, h = bh % a.H;
+            const bool valid = (q0 + row) < a.T;
+            bf16* orow = a.out + ((size_t)b * a.T + q0 + row) * ((size_t)a.H * a.hd) + (size_t)h * a.hd;
 #pragma unroll
-        for (int j8 = 0; j8 < 2; ++j8) {
-          if (c0 + j8 * 8 < a.hd) {  // hd % 8 == 0
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(orow + c0 + j8 * 8) = pk;
+            for (int c8 = 0; c8 < (MULTI ? 16 : 0); ++c8) {
+              if (c8 * 8 < a.hd && valid) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(oacc[c8 * 8 + 0] * inv, oacc[c8 * 8 + 1] * inv);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(oacc[c8 * 8 + 2] * inv, oacc[c8 * 8 + 3] * inv);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(oacc[c8 * 8 + 4] * inv, oacc[c8 * 8 + 5] * inv);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(oacc[c8 * 8 + 6] * inv, oacc[c8 * 8 + 7] * inv);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                *reinterpret_cast<uint4*>(orow + c8 * 8) = pk;
+              }
+            }
           }
         }
       }
@@ -285,36 +379,48 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-static bool g_attn_p_in_tmem = true;
-void set_attention_variant(int p_in_tmem) { g_attn_p_in_tmem = p_in_tmem != 0; }
+// 3-D bf16 tensor map with a caller-chosen swizzle (32-byte swizzle for the compact 16-column tail tiles)
+CUtensorMap make_tmap_3d_bf16_sw(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
+                                 uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
+
+int attention_hdv(int hd) { return ((hd + 1 + 15) / 16) * 16; }
 
 void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
-  VV_CHECK(a.hd % 8 == 0 && a.hdp % 16 == 0 && a.hdv % 16 == 0 && a.hdp >= a.hd && a.hdv >= a.hd,
-           "attention: head_dim must be a multiple of 8; padded dims multiples of 16");
-  VV_CHECK(a.hdp <= 128 && a.hdv <= 128, "attention: head_dim > 128 not supported");
+  VV_CHECK(a.hd % 8 == 0 && a.hdp % 16 == 0 && a.hdv % 16 == 0 && a.hdp >= a.hd && a.hdv >= a.hd + 1,
+           "attention: head_dim % 8; padded dims % 16; hdv must leave room for the row-sum column");
+  VV_CHECK(a.hdp <= 128 && a.hdv <= 128, "attention: head_dim > 112 not supported");
   VV_CHECK(a.T % 8 == 0, "attention: token count must be a multiple of 8");
   VV_CHECK((a.H * a.hd) % 8 == 0, "attention: hidden size must be a multiple of 8");
-  const int nka = (a.hdp + 63) / 64;
-  CUtensorMap tmQ = make_tmap_3d_bf16(a.q, (uint64_t)a.hdp, (uint64_t)a.T, (uint64_t)a.B * a.H, (uint64_t)a.hdp * 2,
+  const AtGeom g = at_geom(a.hdp, a.hdv);
+  const uint64_t BH = (uint64_t)a.B * a.H;
+  CUtensorMap tmQ = make_tmap_3d_bf16(a.q, (uint64_t)a.hdp, (uint64_t)a.T, BH, (uint64_t)a.hdp * 2,
                                       (uint64_t)a.T * a.hdp * 2, 64, AT_BQ, 1);
-  CUtensorMap tmK = make_tmap_3d_bf16(a.k, (uint64_t)a.hdp, (uint64_t)a.T, (uint64_t)a.B * a.H, (uint64_t)a.hdp * 2,
+  CUtensorMap tmK = make_tmap_3d_bf16(a.k, (uint64_t)a.hdp, (uint64_t)a.T, BH, (uint64_t)a.hdp * 2,
                                       (uint64_t)a.T * a.hdp * 2, 64, AT_BKV, 1);
-  CUtensorMap tmV = make_tmap_3d_bf16(a.vt, (uint64_t)a.T, (uint64_t)a.hdv, (uint64_t)a.B * a.H, (uint64_t)a.T * 2,
+  CUtensorMap tmV = make_tmap_3d_bf16(a.vt, (uint64_t)a.T, (uint64_t)a.hdv, BH, (uint64_t)a.T * 2,
                                       (uint64_t)a.hdv * a.T * 2, 64, (uint32_t)a.hdv, 1);
-  const bool ptm = g_attn_p_in_tmem;
-  size_t smem = (size_t)nka * AT_BQ * 128 + (size_t)nka * AT_BKV * 128 + (size_t)4 * a.hdv * 128 +
-                (ptm ? 0 : 4 * AT_BQ * 128) + sizeof(AtBars) + 1024;
+  CUtensorMap tmQt = tmQ, tmKt = tmK;
+  if (g.tail16) {
+    tmQt = make_tmap_3d_bf16_sw(a.q, (uint64_t)a.hdp, (uint64_t)a.T, BH, (uint64_t)a.hdp * 2, (uint64_t)a.T * a.hdp * 2,
+                                16, AT_BQ, 1, 32);
+    tmKt = make_tmap_3d_bf16_sw(a.k, (uint64_t)a.hdp, (uint64_t)a.T, BH, (uint64_t)a.hdp * 2, (uint64_t)a.T * a.hdp * 2,
+                                16, AT_BKV, 1, 32);
+  }
+  const size_t smem = (size_t)((g.q_bytes + 1023) & ~1023) + ((g.k_bytes + 1023) & ~1023) + g.v_bytes + sizeof(AtBars) + 1024;
   VV_CHECK(smem <= 227 * 1024, "attention: shared memory budget exceeded");
-  dim3 grid(cdiv(a.T, AT_BQ), a.B * a.H);
+  int dev, sms;
+  VV_CUDA(cudaGetDevice(&dev));
+  VV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n_items = a.B * a.H * cdiv(a.T, AT_BQ);
+  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  const int grid = std::min(n_items, sms * per_sm);
   const bool multi = a.T > AT_BKV;
   auto go = [&](auto kern) {
     VV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kern<<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, a);
+    kern<<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, tmQt, tmKt, a);
   };
-  if (ptm && !multi) go(k_attention_tc<true, false>);
-  else if (ptm && multi) go(k_attention_tc<true, true>);
-  else if (!ptm && !multi) go(k_attention_tc<false, false>);
-  else go(k_attention_tc<false, true>);
+  if (multi) go(k_attention_tc<true>);
+  else go(k_attention_tc<false>);
   VV_LAUNCH_CHECK();
 }
 

@@ -10,9 +10,6 @@
 #include <string>
 #include <vector>
 
-namespace vv {
-void set_attention_variant(int p_in_tmem);
-}
 using namespace vv;
 
 static thread_local std::string g_err;
@@ -175,7 +172,12 @@ __global__ void k_interleave_bias(const float* __restrict__ in, float* __restric
   if (r >= 2 * S) return;
   out[r] = in[(r & 1) ? S + (r >> 1) : (r >> 1)];
 }
-__global__ void k_set_scalar(float* dst, const float* src, int idx) { dst[0] = src[idx]; }
+__global__ void k_fill_ones_row(bf16* vt, int BH, int hdv, int row, int T) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= BH * T) return;
+  int bh = idx / T, t = idx % T;
+  vt[((size_t)bh * hdv + row) * T + t] = __float2bfloat16_rn(1.0f);
+}
 
 static void pack_bf16(vavae_engine* e, const float* src, bf16* dst, int rows, int K, int ldo, int interleave_S,
                       cudaStream_t s) {
@@ -206,14 +208,14 @@ static void derive(vavae_engine* e) {
   e->NM = e->L * e->nmod * e->D + 2 * e->D;
   e->Spad = ((e->S + 7) / 8) * 8;
   e->hdp = ((e->hd + 15) / 16) * 16;
-  e->hdv = ((e->hd + 15) / 16) * 16;
+  e->hdv = attention_hdv(e->hd);
   e->fp32 = c.precision == VAVAE_PREC_FP32;
   VV_CHECK(c.precision == VAVAE_PREC_FP32 || c.precision == VAVAE_PREC_BF16, "unknown precision mode");
   VV_CHECK(e->D % 4 == 0 && e->D <= 2048, "hidden_size must be a multiple of 4 and <= 2048");
   VV_CHECK(e->hd % 2 == 0, "head_dim must be even (RoPE pairs)");
   VV_CHECK((e->img * e->img) % 4 == 0, "latent H*W must be a multiple of 4");
   if (!e->fp32) {
-    VV_CHECK(e->D % 16 == 0 && e->hd % 8 == 0 && e->hd <= 128, "bf16 path: hidden % 16, head_dim % 8, head_dim <= 128");
+    VV_CHECK(e->D % 16 == 0 && e->hd % 8 == 0 && e->hd <= 112, "bf16 path: hidden % 16, head_dim % 8, head_dim <= 112");
     VV_CHECK(e->T % 8 == 0, "bf16 path: token count must be a multiple of 8");
   }
 }
@@ -367,6 +369,9 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
     e->q_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
     e->k_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
     e->vt_h = e->alloc<bf16>((size_t)R * e->H * e->hdv * T, true);
+    // row hd of every (row, head) block of v^T is all ones: column hd of P V then is the softmax row sum
+    k_fill_ones_row<<<cdiv(R * e->H * T, 256), 256, 0, s>>>(e->vt_h, R * e->H, e->hdv, e->hd, T);
+    VV_LAUNCH_CHECK();
     e->O_h = e->alloc<bf16>(M * D);
     e->Hh_h = e->alloc<bf16>(M * e->Spad, true);
   }
@@ -851,18 +856,13 @@ int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void
     vv::g_counter = nullptr;
     TcAttnArgs a;
     a.q = (const bf16*)q; a.k = (const bf16*)k; a.vt = (const bf16*)vt; a.out = (bf16*)out;
-    a.B = B; a.H = H; a.T = T; a.hd = hd; a.hdp = ((hd + 15) / 16) * 16; a.hdv = a.hdp;
+    a.B = B; a.H = H; a.T = T; a.hd = hd; a.hdp = ((hd + 15) / 16) * 16; a.hdv = attention_hdv(hd);
     launch_attention_tc(a, (cudaStream_t)stream);
     return 0;
   } catch (const std::exception& ex) {
     g_err = ex.what();
     return 1;
   }
-}
-
-int vavae_set_attention_variant(int p_in_tmem) {
-  vv::set_attention_variant(p_in_tmem);
-  return 0;
 }
 
 int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work, void* stream) {

@@ -61,6 +61,25 @@ CUtensorMap make_tmap_3d_bf16(const void* base, uint64_t d0, uint64_t d1, uint64
   return m;
 }
 
+CUtensorMap make_tmap_3d_bf16_sw(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
+                                 uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  VV_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && pitch1_bytes % 16 == 0 && pitch2_bytes % 16 == 0,
+           "tensor map alignment");
+  VV_CHECK((int)b0 * 2 <= swizzle_bytes, "tensor map: inner box wider than the swizzle span");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(3d, swizzle) failed with code " + std::to_string((int)r));
+  return m;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;

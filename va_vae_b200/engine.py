@@ -23,7 +23,7 @@ EXPORTS = [
     "vavae_abi_version", "vavae_last_error", "vavae_create", "vavae_destroy", "vavae_load_weight", "vavae_finalize",
     "vavae_forward", "vavae_forward_with_cfg", "vavae_sample_ode", "vavae_sample_ode_host", "vavae_launch_count",
     "vavae_device_bytes", "vavae_test_gemm_bf16", "vavae_test_attention_bf16", "vavae_time_kernel",
-    "vavae_set_attention_variant", "vavae_profile_begin", "vavae_profile_end",
+    "vavae_profile_begin", "vavae_profile_end",
 ]
 
 
@@ -69,7 +69,6 @@ def load_library() -> ctypes.CDLL:
     lib.vavae_test_attention_bf16.argtypes = [c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_void]
     lib.vavae_time_kernel.argtypes = [c_void, ctypes.c_char_p, c_int, c_int, ctypes.POINTER(c_float),
                                       ctypes.POINTER(ctypes.c_double), c_void]
-    lib.vavae_set_attention_variant.argtypes = [c_int]
     lib.vavae_profile_begin.argtypes = [c_void, ctypes.c_char_p]
     lib.vavae_profile_end.argtypes = [c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_double)]
@@ -253,12 +252,16 @@ def test_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
-def test_attention_bf16(q, k, vt, hd: int, p_in_tmem: bool = True) -> torch.Tensor:
-    """q,k: (B,H,T,hdp) bf16; vt: (B,H,hdv,T) bf16 -> (B*T, H*hd) bf16."""
+def attention_hdv(hd: int) -> int:
+    """Rows of the transposed-V operand: head_dim + the ones row, rounded up to 16."""
+    return (hd + 1 + 15) // 16 * 16
+
+
+def test_attention_bf16(q, k, vt, hd: int) -> torch.Tensor:
+    """q,k: (B,H,T,hdp) bf16; vt: (B,H,hdv,T) bf16 (row hd = ones) -> (B*T, H*hd) bf16."""
     lib = load_library()
     B, H, T, _ = q.shape
     out = torch.empty(B * T, H * hd, device=q.device, dtype=torch.bfloat16)
-    lib.vavae_set_attention_variant(1 if p_in_tmem else 0)
     with torch.cuda.device(q.device):
         _check(lib.vavae_test_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, T, hd,
                                              ctypes.c_void_p(_stream(q.device))))
