@@ -44,6 +44,10 @@ def sample_sharded(sample_local: Callable[[torch.Tensor, torch.Tensor], torch.Te
         out = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
-    parts = [torch.empty((b - a,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for a, b in sizes]
-    dist.all_gather(parts, local.contiguous(), group=group)
-    return torch.cat(parts, 0)
+    # uneven shards: pad every shard to the largest one so a single equal-size all-gather still suffices
+    m = max(b - a for a, b in sizes)
+    padded = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * m: r * m + (b - a)] for r, (a, b) in enumerate(sizes)], 0)
