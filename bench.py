@@ -268,7 +268,7 @@ def run_engine(args):
                              f"{args.method}+CFG = {n_evals} evals (cfg {scale}, shift {shift}, 3 guided channels)",
                     parallelism=f"dp{world} (samples sharded, CFG pair per GPU, one all-gather of final latents)",
                     weights="random init (oracle.init_state_dict seed 0)", l2="flushed between steps (256 MiB write)",
-                    chunk_rows=args.chunk or 128, tflops_per_gpu_whole_step=achieved_total,
+                    chunk_rows=args.chunk or 512, tflops_per_gpu_whole_step=achieved_total,
                     frac_of_sustained_peak_whole_step=achieved_total / pk["tflops_sustained"]),
         clocks=clk,
         e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(zz.numel() * 4 + yy.numel() * 8) * world,
@@ -300,7 +300,7 @@ def run_engine(args):
 
 
 def eng_chunk(eng, args):
-    return args.chunk or 128
+    return args.chunk or 512
 
 
 if __name__ == "__main__":

@@ -30,6 +30,10 @@ struct vavae_engine {
   int device = 0;
   // derived sizes
   int D, T, H, hd, S, L, C, p, img, Cout, Ckeep, nmod, NM, Spad, hdp, hdv, grid_hw, Pout;
+  int NMx = 0;      // row pitch of `mod`: NM modulation columns + (fused norm) per-layer shift.W^T+bias columns
+  int N1 = 0;       // output columns of the first MLP GEMM (2S rounded to 4 for SwiGLU, S for GELU)
+  bool fuse = false;  // RMSNorm+modulate folded into the producing / consuming GEMM epilogues
+  float *part1 = nullptr, *part2 = nullptr;  // per-row partial sums of squares [n_parts, M]
   bool fp32;
   bool finalized = false;
   int chunk_rows = 0;
@@ -210,6 +214,9 @@ static void derive(vavae_engine* e) {
   e->hdp = ((e->hd + 15) / 16) * 16;
   e->hdv = attention_hdv(e->hd);
   e->fp32 = c.precision == VAVAE_PREC_FP32;
+  e->N1 = c.use_swiglu ? ((2 * e->S + 3) / 4) * 4 : e->S;
+  e->fuse = !e->fp32 && c.use_rmsnorm && (e->T % 32 == 0);
+  e->NMx = e->NM + ((e->fuse && !c.wo_shift) ? e->L * (3 * e->D + e->N1) : 0);
   VV_CHECK(c.precision == VAVAE_PREC_FP32 || c.precision == VAVAE_PREC_BF16, "unknown precision mode");
   VV_CHECK(e->D % 4 == 0 && e->D <= 2048, "hidden_size must be a multiple of 4 and <= 2048");
   VV_CHECK(e->hd % 2 == 0, "head_dim must be even (RoPE pairs)");
@@ -221,6 +228,8 @@ static void derive(vavae_engine* e) {
 }
 
 // --------------------------------------------------------------------------------------------- finalize
+static void gemm32(const float* A, int lda, const float* Wt, const float* bias, float* Cc, int ldc, int M, int N, int K,
+                   int epi, cudaStream_t s);
 static void finalize(vavae_engine* e, cudaStream_t s) {
   const int D = e->D, L = e->L, S = e->S, C = e->C, p = e->p, T = e->T, hd = e->hd;
   const vavae_config_t& c = e->cfg;
@@ -281,9 +290,9 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
   k_transpose<<<cdiv(D * Cpp, 256), 256, 0, s>>>(e->W("x_embedder.proj.weight").d, e->embed_wT, D, Cpp);
   VV_LAUNCH_CHECK();
   // batched adaLN: one [NM, D] matrix = every block's modulation Linear followed by the final layer's
-  e->ada_b = e->alloc<float>(e->NM);
-  if (e->fp32) e->ada_w = e->alloc<float>((size_t)e->NM * D);
-  else e->ada_w_h = e->alloc<bf16>((size_t)e->NM * D);
+  e->ada_b = e->alloc<float>(e->NMx, true);
+  if (e->fp32) e->ada_w = e->alloc<float>((size_t)e->NMx * D);
+  else e->ada_w_h = e->alloc<bf16>((size_t)e->NMx * D, true);
   for (int i = 0; i <= L; ++i) {
     const bool fin = i == L;
     const Weight& aw = e->W(fin ? std::string("final_layer.adaLN_modulation.1.weight") : blk(i, "adaLN_modulation.1.weight"));
@@ -293,6 +302,43 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
     VV_CUDA(cudaMemcpyAsync(e->ada_b + row0, ab.d, (size_t)rows * 4, cudaMemcpyDeviceToDevice, s));
     if (e->fp32) VV_CUDA(cudaMemcpyAsync(e->ada_w + row0 * D, aw.d, (size_t)rows * D * 4, cudaMemcpyDeviceToDevice, s));
     else pack_bf16(e, aw.d, e->ada_w_h + row0 * D, rows, D, D, 0, s);
+  }
+  if (e->fuse && !c.wo_shift) {
+    // Fused-norm consumers need sp[b,n] = shift[b,:].W[n,:] + bias[n].  shift = silu(c).Wa_shift^T + ba_shift, so
+    // sp = silu(c).(W.Wa_shift)^T + (W.ba_shift + bias): extra output columns of the single adaLN GEMM.
+    const int N1 = e->N1;
+    const int maxN = std::max(3 * D, 2 * S);
+    float* waT = e->alloc<float>((size_t)D * D);
+    float* wc = e->alloc<float>((size_t)maxN * D);
+    float* bc = e->alloc<float>(maxN);
+    for (int i = 0; i < L; ++i) {
+      const float* Wa = e->W(blk(i, "adaLN_modulation.1.weight")).d;   // rows: shift_msa | scale_msa | gate_msa | shift_mlp | ...
+      const float* ba = e->W(blk(i, "adaLN_modulation.1.bias")).d;
+      const size_t row0 = (size_t)e->NM + (size_t)i * (3 * D + N1);
+      for (int which = 0; which < 2; ++which) {
+        const int chunk = which == 0 ? 0 : 3;                           // shift_msa, shift_mlp (lightningdit.py:246)
+        const float* Wl = which == 0 ? e->W(blk(i, "attn.qkv.weight")).d
+                                     : e->W(blk(i, c.use_swiglu ? "mlp.w12.weight" : "mlp.fc1.weight")).d;
+        const float* bl = which == 0 ? e->W(blk(i, "attn.qkv.bias")).d
+                                     : e->W(blk(i, c.use_swiglu ? "mlp.w12.bias" : "mlp.fc1.bias")).d;
+        const int Nl = which == 0 ? 3 * D : (c.use_swiglu ? 2 * S : S);
+        k_transpose<<<cdiv(D * D, 256), 256, 0, s>>>(Wa + (size_t)chunk * D * D, waT, D, D);
+        VV_LAUNCH_CHECK();
+        gemm32(Wl, D, waT, nullptr, wc, D, Nl, D, D, F32_EPI_NONE, s);                    // wc[n,j] = sum_k W[n,k] Wa_shift[k,j]
+        gemm32(ba + (size_t)chunk * D, D, Wl, bl, bc, Nl, 1, Nl, D, F32_EPI_NONE, s);    // bc[n] = W[n,:].ba_shift + bias[n]
+        const size_t r0 = row0 + (which == 0 ? 0 : 3 * D);
+        const bool il = which == 1 && c.use_swiglu;
+        pack_bf16(e, wc, e->ada_w_h + r0 * D, Nl, D, D, il ? S : 0, s);
+        if (il) {
+          k_interleave_bias<<<cdiv(2 * S, 256), 256, 0, s>>>(bc, e->ada_b + r0, S);
+          VV_LAUNCH_CHECK();
+        } else {
+          VV_CUDA(cudaMemcpyAsync(e->ada_b + r0, bc, (size_t)Nl * 4, cudaMemcpyDeviceToDevice, s));
+        }
+      }
+    }
+    VV_CUDA(cudaStreamSynchronize(s));
+    e->release(waT); e->release(wc); e->release(bc);
   }
   if (!e->fp32) {
     e->lw.resize(L);
@@ -339,7 +385,7 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
   }
 
   // ---- workspace
-  int R = c.max_chunk_rows > 0 ? c.max_chunk_rows : (e->fp32 ? 16 : 128);
+  int R = c.max_chunk_rows > 0 ? c.max_chunk_rows : (e->fp32 ? 16 : 512);
   if (R % 2) R += 1;
   e->chunk_rows = R;
   const size_t M = (size_t)R * T;
@@ -347,7 +393,7 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
   e->tf = e->alloc<float>((size_t)R * 256);
   e->th = e->alloc<float>((size_t)R * D);
   e->cbuf = e->alloc<float>((size_t)R * D);
-  e->mod = e->alloc<float>((size_t)R * e->NM);
+  e->mod = e->alloc<float>((size_t)R * e->NMx);
   e->st = e->alloc<float>(4);
   if (e->fp32) {
     e->sc_f = e->alloc<float>((size_t)R * D);
@@ -365,6 +411,10 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
     e->sc_h = e->alloc<bf16>((size_t)R * D);
     e->A_h = e->alloc<bf16>(M * D);
     e->A3_h = e->alloc<bf16>(M * 3 * D);
+    if (e->fuse) {
+      e->part1 = e->alloc<float>(32 * M, true);
+      e->part2 = e->alloc<float>(32 * M, true);
+    }
     // padding columns d in [hd, hdp) of q/k and rows [hd, hdv) of v^T stay zero forever (never written)
     e->q_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
     e->k_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
@@ -399,7 +449,7 @@ static ModOff mod_offsets(const vavae_engine* e, int layer) {
 static void norm_mod(vavae_engine* e, const float* w, int shift_off, int scale_off, int M, cudaStream_t s,
                      bool split3 = false) {
   NormModArgs n;
-  n.X = e->X; n.w = w; n.mod = e->mod; n.mod_ld = e->NM; n.shift_off = shift_off; n.scale_off = scale_off;
+  n.X = e->X; n.w = w; n.mod = e->mod; n.mod_ld = e->NMx; n.shift_off = shift_off; n.scale_off = scale_off;
   n.out = e->fp32 ? (void*)e->A_f : (split3 ? (void*)e->A3_h : (void*)e->A_h);
   n.ldo = split3 ? 3 * e->D : e->D; n.M = M; n.D = e->D; n.T = e->T;
   n.out_bf16 = e->fp32 ? 0 : 1;
@@ -437,10 +487,10 @@ static void conditioning(vavae_engine* e, int rows, const RowMap& rm, const floa
   launch_gemm_f32(g, s);
   // every adaLN modulation of the network in one GEMM: mod[rows, NM]
   if (e->fp32) {
-    gemm32(e->sc_f, D, e->ada_w, e->ada_b, e->mod, e->NM, rows, e->NM, D, F32_EPI_NONE, s);
+    gemm32(e->sc_f, D, e->ada_w, e->ada_b, e->mod, e->NMx, rows, e->NMx, D, F32_EPI_NONE, s);
   } else {
-    TcGemmArgs a = tc_args(e->sc_h, D, e->ada_w_h, D, rows, e->NM, D, TC_EPI_BIAS_F32, e->ada_b);
-    a.out = e->mod; a.ldo = e->NM;
+    TcGemmArgs a = tc_args(e->sc_h, D, e->ada_w_h, D, rows, e->NMx, D, TC_EPI_BIAS_F32, e->ada_b);
+    a.out = e->mod; a.ldo = e->NMx;
     launch_gemm_tc(a, s);
   }
 }
@@ -459,6 +509,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
   const float* rcos = c.use_rope ? e->W("feat_rope.freqs_cos").d : nullptr;
   const float* rsin = c.use_rope ? e->W("feat_rope.freqs_sin").d : nullptr;
 
+  int np_proj = 0, np_w3 = 0;  // number of partial-sum slots the last proj / w3 epilogue wrote
   for (int i = 0; i < L; ++i) {
     const ModOff mo = mod_offsets(e, i);
     const float* n1 = c.use_rmsnorm ? e->W(blk(i, "norm1.weight")).d : nullptr;
@@ -473,7 +524,14 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       }
     }
     // ---- attention branch
-    {
+    // With the fused norm (bf16 + RMSNorm + T % 32 == 0) only the first norm of the network runs as a kernel: every
+    // gated-residual epilogue emits the next GEMM's un-normalised bf16 operand plus per-row partial sums of
+    // squares, and the consuming GEMM applies 1/rms per row and the per-sample shift.W^T + bias vector.
+    const bool fuse = e->fuse;
+    const int sp_stride = 3 * D + e->N1;
+    const float* sp_qkv = (fuse && !c.wo_shift) ? e->mod + e->NM + (size_t)i * sp_stride : nullptr;
+    const float* sp_mlp = (fuse && !c.wo_shift) ? sp_qkv + 3 * D : nullptr;
+    if (!fuse || i == 0) {
       ProfScope ps(e, PK_NORM, (double)M * D * (e->fp32 ? 8.0 : 6.0), s);
       norm_mod(e, n1, mo.shift_msa, mo.scale_msa, M, s);
     }
@@ -488,11 +546,16 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       launch_attention_f32(e->q_f, e->k_f, e->v_f, e->O_f, rows, H, T, hd, s);
       gemm32(e->O_f, D, e->W(blk(i, "attn.proj.weight")).d, e->W(blk(i, "attn.proj.bias")).d, e->Y_f, D, M, D, D,
              F32_EPI_NONE, s);
-      launch_gated_residual_f32(e->X, e->Y_f, e->mod, e->NM, mo.gate_msa, M, D, T, s);
+      launch_gated_residual_f32(e->X, e->Y_f, e->mod, e->NMx, mo.gate_msa, M, D, T, s);
     } else {
-      TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].qkv, D, M, 3 * D, D, TC_EPI_QKV, e->W(blk(i, "attn.qkv.bias")).d);
+      const float* bqkv = e->W(blk(i, "attn.qkv.bias")).d;
+      TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].qkv, D, M, 3 * D, D, TC_EPI_QKV, bqkv);
       a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
       a.kn_b = knb; a.qk_rms = c.use_rmsnorm; a.H = H; a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
+      if (fuse && i > 0) {
+        a.in_part = e->part2; a.in_nparts = np_w3; a.in_dim = D;
+        a.sp = sp_qkv ? sp_qkv : bqkv; a.sp_ld = sp_qkv ? e->NMx : 0;
+      }
       {
         ProfScope ps(e, PK_QKV, 2.0 * M * 3.0 * D * D, s);
         launch_gemm_tc(a, s);
@@ -505,14 +568,21 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
         launch_attention_tc(at, s);
       }
       TcGemmArgs pr = tc_args(e->O_h, D, e->lw[i].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(i, "attn.proj.bias")).d);
-      pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NM; pr.gate_off = mo.gate_msa; pr.T = T;
+      pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NMx; pr.gate_off = mo.gate_msa; pr.T = T;
+      if (fuse) {  // emit the operand of this block's MLP norm (norm2)
+        pr.nx_w = n2; pr.nx_scale_off = mo.scale_mlp; pr.nx_A = e->A_h; pr.nx_part = e->part1;
+        np_proj = 2 * cdiv(D, gemm_tc_pick_bn(pr));
+      }
       {
         ProfScope ps(e, PK_PROJ, 2.0 * M * (double)D * D, s);
         launch_gemm_tc(pr, s);
       }
     }
     // ---- MLP branch
-    norm_mod(e, n2, mo.shift_mlp, mo.scale_mlp, M, s);
+    if (!fuse) {
+      ProfScope ps(e, PK_NORM, (double)M * D * (e->fp32 ? 8.0 : 6.0), s);
+      norm_mod(e, n2, mo.shift_mlp, mo.scale_mlp, M, s);
+    }
     if (e->fp32) {
       if (c.use_swiglu) {
         gemm32(e->A_f, D, e->W(blk(i, "mlp.w12.weight")).d, e->W(blk(i, "mlp.w12.bias")).d, e->U_f, 2 * S, M, 2 * S, D,
@@ -526,22 +596,27 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
         gemm32(e->Hh_f, S, e->W(blk(i, "mlp.fc2.weight")).d, e->W(blk(i, "mlp.fc2.bias")).d, e->Y_f, D, M, D, S,
                F32_EPI_NONE, s);
       }
-      launch_gated_residual_f32(e->X, e->Y_f, e->mod, e->NM, mo.gate_mlp, M, D, T, s);
+      launch_gated_residual_f32(e->X, e->Y_f, e->mod, e->NMx, mo.gate_mlp, M, D, T, s);
     } else {
-      if (c.use_swiglu) {
-        TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, ((2 * S + 3) / 4) * 4, D, TC_EPI_SWIGLU, e->lw[i].b1);
-        a.out = e->Hh_h; a.ldo = e->Spad;
-        ProfScope ps(e, PK_W12, 2.0 * M * 2.0 * S * D, s);
-        launch_gemm_tc(a, s);
-      } else {
-        TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, S, D, TC_EPI_GELU_BF16, e->lw[i].b1);
-        a.out = e->Hh_h; a.ldo = e->Spad;
-        ProfScope ps(e, PK_W12, 2.0 * M * (double)S * D, s);
+      {
+        TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].w1, D, M, e->N1, D, c.use_swiglu ? TC_EPI_SWIGLU : TC_EPI_GELU_BF16,
+                               e->lw[i].b1);
+        a.out = e->Hh_h; a.ldo = e->Spad; a.T = T;
+        if (fuse) {
+          a.in_part = e->part1; a.in_nparts = np_proj; a.in_dim = D;
+          a.sp = sp_mlp ? sp_mlp : e->lw[i].b1; a.sp_ld = sp_mlp ? e->NMx : 0;
+        }
+        ProfScope ps(e, PK_W12, 2.0 * M * (c.use_swiglu ? 2.0 : 1.0) * S * D, s);
         launch_gemm_tc(a, s);
       }
       const float* b2 = e->W(blk(i, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d;
       TcGemmArgs a = tc_args(e->Hh_h, e->Spad, e->lw[i].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL, b2);
-      a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NM; a.gate_off = mo.gate_mlp; a.T = T;
+      a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NMx; a.gate_off = mo.gate_mlp; a.T = T;
+      if (fuse && i + 1 < L) {  // emit the operand of the next block's attention norm (norm1)
+        const ModOff nmo = mod_offsets(e, i + 1);
+        a.nx_w = e->W(blk(i + 1, "norm1.weight")).d; a.nx_scale_off = nmo.scale_msa; a.nx_A = e->A_h; a.nx_part = e->part2;
+        np_w3 = 2 * cdiv(D, gemm_tc_pick_bn(a));
+      }
       {
         ProfScope ps(e, PK_W3, 2.0 * M * (double)S * D, s);
         launch_gemm_tc(a, s);
@@ -891,7 +966,7 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     *work = 2.0 * M * (double)D * D;
     fn = [&] {
       TcGemmArgs pr = tc_args(e->O_h, D, e->lw[0].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(0, "attn.proj.bias")).d);
-      pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NM; pr.gate_off = mo.gate_msa; pr.T = T;
+      pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NMx; pr.gate_off = mo.gate_msa; pr.T = T;
       launch_gemm_tc(pr, s);
     };
   } else if (k == "gemm_w12") {
@@ -907,7 +982,7 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     fn = [&] {
       TcGemmArgs a = tc_args(e->Hh_h, e->Spad, e->lw[0].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL,
                              e->W(blk(0, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d);
-      a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NM; a.gate_off = mo.gate_mlp; a.T = T;
+      a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NMx; a.gate_off = mo.gate_mlp; a.T = T;
       launch_gemm_tc(a, s);
     };
   } else if (k == "attention") {

@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // Per-row statistics over one head's hd accumulator columns (re-read from TMEM, 8 columns at a time).
 // Called with the warp converged (head boundaries depend on the column only).
 __device__ __noinline__ void qk_head_stats(uint32_t tbase, int hc0, int n0, int hd, const float* __restrict__ bias,
-                                           int rms, float& mean, float& rstd) {
+                                           float in_scale, int rms, float& mean, float& rstd) {
   float s1 = 0.f, s2 = 0.f;
   for (int dd = 0; dd < hd; dd += 8) {
     uint32_t t8[8];
@@ -111,7 +111,7 @@ __device__ __noinline__ void qk_head_stats(uint32_t tbase, int hc0, int n0, int 
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float x = __uint_as_float(t8[e]) + bias[n0 + hc0 + dd + e];
+      float x = __uint_as_float(t8[e]) * in_scale + bias[n0 + hc0 + dd + e];
       s1 += x;
       s2 += x * x;
     }
@@ -238,6 +238,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int m0 = m_blk * TC_BM, n0 = n_blk * BN;
       const int wrow0 = m0 + q * 32;     // first row of this warp
       const int my_row = wrow0 + lane;   // thread == row domain
+      const int wb = wrow0 / a.T, wt0 = wrow0 - wb * a.T;  // sample / first token of the warp (valid if rows_one_sample)
       int n_chunks = (min(BN, a.N - n0) + CW - 1) / CW;
 
       // ---- prefetch for the gated-residual epilogue: the fp32 residual tile is loaded one chunk ahead so the
@@ -255,6 +256,44 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       };
       prefetch_x(half);
+      // fused-norm consumer: this row's 1/rms from the producer's partial sums (fixed summation order)
+      float in_rstd = 1.f;
+      if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part) {
+        float ssum = 0.f;
+        if (my_row < a.M)
+          for (int pi = 0; pi < a.in_nparts; ++pi) ssum += a.in_part[(size_t)pi * a.M + my_row];
+        in_rstd = rsqrtf(ssum / (float)a.in_dim + 1e-6f);
+      }
+      // per-row bias source: per-sample vector sp[b,:] when the norm is fused, else the plain bias
+      const float* brow = a.bias;
+      if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part)
+        brow = a.sp + (size_t)(min(my_row, a.M - 1) / a.T) * a.sp_ld;
+      const float* bwarp = a.bias;  // same, for the warp's (single) sample in the row-wise pass
+      if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part)
+        bwarp = a.sp + (size_t)min(wb, (a.M - 1) / a.T) * a.sp_ld;
+      float ssacc[LPR];
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
+
+      // Per-column vectors of a chunk in the row-wise pass: bias (or the fused per-sample sp vector), and for the
+      // gated residual the gate and the next norm's w*(1+scale).  sp / gate / scale live in the big `mod` matrix
+      // (DRAM/L2 latency), so they are software-pipelined one chunk ahead like the residual tile.
+      auto load_vecs = [&](int c, float4& bbv, float4& gv, float4& cwv) {
+        bbv = gv = cwv = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int colv = n0 + c * CW + pcc;
+        if (c >= n_chunks || colv >= a.N || EPI == TC_EPI_FINAL) return;
+        if (a.bias && (EPI != TC_EPI_QKV || !a.qn_w)) bbv = *reinterpret_cast<const float4*>(bwarp + colv);
+        if (EPI == TC_EPI_GATED_RESIDUAL && rows_one_sample && wrow0 < a.M) {
+          gv = *reinterpret_cast<const float4*>(a.mod + (size_t)wb * a.mod_ld + a.gate_off + colv);
+          if (a.nx_w) {
+            const float4 w4 = *reinterpret_cast<const float4*>(a.nx_w + colv);
+            const float4 s4 = *reinterpret_cast<const float4*>(a.mod + (size_t)wb * a.mod_ld + a.nx_scale_off + colv);
+            cwv = make_float4(w4.x * (1.f + s4.x), w4.y * (1.f + s4.y), w4.z * (1.f + s4.z), w4.w * (1.f + s4.w));
+          }
+        }
+      };
+      float4 bb_n, g1_n, cw_n;
+      load_vecs(half, bb_n, g1_n, cw_n);
 
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after();
@@ -275,7 +314,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int ps = 0; ps < LPR; ++ps) xcur[ps] = xpre[ps];
           prefetch_x(c + 2);
         }
+        // per-column vectors of this chunk were requested one chunk ago; request the next chunk's now
+        const float4 bb = bb_n, g1 = g1_n, cw = cw_n;
+        load_vecs(c + 2, bb_n, g1_n, cw_n);
         ptx::tmem_ld_wait();
+        if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * in_rstd);
+        }
 
         if (EPI == TC_EPI_FINAL) {
           // unpatchify (lightningdit.py:376-389): token-major column (pa*p+pb)*Cout + c -> NCHW; lanes are
@@ -314,7 +360,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (col < a.N) {
                   const int rem = col - 2 * D, h = rem / a.hd, d = rem % a.hd;
                   a.vt[(((size_t)b * a.H + h) * a.hdv + d) * a.T + t] =
-                      __float2bfloat16_rn(__uint_as_float(r[j]) + a.bias[col]);
+                      __float2bfloat16_rn(__uint_as_float(r[j]) + brow[col]);
                 }
               }
             }
@@ -327,7 +373,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (nw) {
             float bj[CW];
 #pragma unroll
-            for (int j = 0; j < CW; ++j) bj[j] = a.bias[colc + j];  // independent loads, issued back to back
+            for (int j = 0; j < CW; ++j) bj[j] = brow[colc + j];  // independent loads, issued back to back
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
               const int col = colc + j;
@@ -335,7 +381,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               const int rem = col - which * D, h = rem / a.hd, d = rem % a.hd;
               if (h != qk_head) {
                 qk_head = h;
-                qk_head_stats(tbase, which * D + h * a.hd - n0, n0, a.hd, a.bias, a.qk_rms, qk_mean, qk_rstd);
+                qk_head_stats(tbase, which * D + h * a.hd - n0, n0, a.hd, brow, in_rstd, a.qk_rms, qk_mean, qk_rstd);
               }
               v = (v - qk_mean) * qk_rstd * nw[d] + (nb ? nb[d] : 0.f);
               r[j] = __float_as_uint(v);
@@ -356,15 +402,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           // V^T fast path: lane owns head-dim column d and 8 consecutive tokens -> one 16-byte store;
           // a warp instruction writes 8 columns x 64 contiguous bytes of (B,H,hdv,T)
           const int D = a.H * a.hd;
-          const int b = wrow0 / a.T, t0 = wrow0 % a.T;
+          const int b = wb, t0 = wt0;
           const int tg = lane & 3;
+          float bv4[4];
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int colb = n0 + c0 + ps * 8 + (lane >> 2);
+            bv4[ps] = colb < a.N ? bwarp[colb] : 0.f;  // all four issued before the first store
+          }
 #pragma unroll
           for (int ps = 0; ps < 4; ++ps) {
             const int j = ps * 8 + (lane >> 2);
             const int col = n0 + c0 + j;
             if (col < a.N && wrow0 + tg * 8 < a.M) {
               const int rem = col - 2 * D, h = rem / a.hd, d = rem % a.hd;
-              const float bv = a.bias[col];
+              const float bv = bv4[ps];
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = st[(tg * 8 + e) * (CW + 4) + j] + bv;
@@ -377,14 +429,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
         const int col = n0 + c0 + pcc;  // this lane's 4 columns in every pass
         const bool col_ok = col < a.N;
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias && col_ok && (EPI != TC_EPI_QKV || !a.qn_w)) bb = *reinterpret_cast<const float4*>(a.bias + col);
 
         if (EPI == TC_EPI_GATED_RESIDUAL) {
           // x = x + gate.unsqueeze(1) * f(...)   lightningdit.py:248-249 ; x was prefetched one chunk ahead
-          float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rows_one_sample && col_ok && wrow0 < a.M)
-            g1 = *reinterpret_cast<const float4*>(a.mod + (size_t)(wrow0 / a.T) * a.mod_ld + a.gate_off + col);
+          // g1 = gate, cw = w_norm * (1 + scale) of the norm that follows this residual update (both prefetched)
 #pragma unroll
           for (int ps = 0; ps < LPR; ++ps) {
             const int rr = ps * RPP + prow;
@@ -398,6 +446,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             x.x = fmaf(g.x, v.x + bb.x, x.x); x.y = fmaf(g.y, v.y + bb.y, x.y);
             x.z = fmaf(g.z, v.z + bb.z, x.z); x.w = fmaf(g.w, v.w + bb.w, x.w);
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = x;
+            if (a.nx_w) {
+              ssacc[ps] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+              *reinterpret_cast<uint2*>(a.nx_A + (size_t)row * a.ldo + col) =
+                  make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
+            }
           }
           continue;
         }
@@ -412,7 +465,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int ps = 0; ps < LPR; ++ps) {
               const int row = wrow0 + ps * RPP + prow;
-              const int t = row % a.T;
+              const int t = rows_one_sample ? wt0 + ps * RPP + prow : row % a.T;
               const bool ok = row < a.M && col_ok;
               c4[ps] = ok ? *reinterpret_cast<const float4*>(a.cos + (size_t)t * a.hd + d) : make_float4(1.f, 1.f, 1.f, 1.f);
               s4[ps] = ok ? *reinterpret_cast<const float4*>(a.sin + (size_t)t * a.hd + d) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -433,7 +486,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               o.w = v.w * c4[ps].w + v.z * s4[ps].w;
               v = o;
             }
-            const int b = row / a.T, t = row % a.T;
+            const int b = rows_one_sample ? wb : row / a.T;
+            const int t = rows_one_sample ? wt0 + rr : row % a.T;
             bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)b * a.H + h) * a.T + t) * a.hdp + d;
             *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
           }
@@ -460,6 +514,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint32_t pk = pack_bf16(silu_fast(v.x) * v.y, silu_fast(v.z) * v.w);
             *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo + (col >> 1)) = pk;
           }
+        }
+      }
+      if (EPI == TC_EPI_GATED_RESIDUAL && a.nx_w) {
+        // per-row partial sum of squares over this warp's column chunks of this tile -> fixed slot (no atomics)
+#pragma unroll
+        for (int ps = 0; ps < LPR; ++ps) {
+          float v = ssacc[ps];
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          const int row = wrow0 + ps * RPP + prow;
+          if ((lane % LPR) == 0 && row < a.M) a.nx_part[(size_t)(n_blk * 2 + half) * a.M + row] = v;
         }
       }
       // release this accumulator stage to the MMA warp

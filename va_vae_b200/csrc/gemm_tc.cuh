@@ -36,6 +36,20 @@ struct TcGemmArgs {
   // final
   int p, Cout, Ckeep, img;
   RowMap rm;
+  // ---- RMSNorm + modulate fused across GEMMs (requires T % 32 == 0) --------------------------------------
+  // producer side (TC_EPI_GATED_RESIDUAL): besides x_new, write the NEXT GEMM's operand
+  //   nx_A[row, col] = bf16(x_new * nx_w[col] * (1 + mod[b, nx_scale_off + col]))        (un-normalised)
+  // and per-row partial sums of x_new^2: nx_part[(n_tile*2 + half) * M + row]
+  const float* nx_w;
+  int nx_scale_off;
+  bf16* nx_A;
+  float* nx_part;
+  // consumer side (QKV / SWIGLU / GELU): the accumulator row is scaled by rstd = rsqrt(sum(in_part)/in_dim + 1e-6)
+  // and `sp[b, n]` (= shift[b,:] . W[n,:] + bias[n], fp32, row pitch sp_ld) replaces the bias
+  const float* in_part;
+  int in_nparts, in_dim;
+  const float* sp;
+  int sp_ld;
 };
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);

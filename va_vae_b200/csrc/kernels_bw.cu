@@ -106,8 +106,10 @@ void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowM
 // RMSNorm / LayerNorm + adaLN modulate, one warp per token row, row kept in registers.
 // rmsnorm.py:63,76-77 ; lightningdit.py:26-30.   out = norm(x)*w*(1+scale)+shift
 // ------------------------------------------------------------------------------------------------
-constexpr int NM_MAXV = 16;  // float4 per lane -> D <= 2048
-template <bool OUT_BF16>
+constexpr int NM_MAXV_LIMIT = 16;  // float4 per lane -> D <= 2048
+// NM_MAXV (float4 registers per lane holding the row) is a template parameter so small hidden sizes keep the
+// register count - and with it the number of rows in flight per SM - where a bandwidth kernel needs it.
+template <bool OUT_BF16, int NM_MAXV>
 __global__ void __launch_bounds__(256) k_norm_modulate(NormModArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -188,14 +190,24 @@ __global__ void __launch_bounds__(256) k_norm_modulate(NormModArgs a) {
   }
 }
 void launch_norm_modulate(const NormModArgs& a, cudaStream_t s) {
-  VV_CHECK(a.D % 4 == 0 && a.D <= NM_MAXV * 128, "norm_modulate: hidden size must be a multiple of 4 and <= 2048");
+  VV_CHECK(a.D % 4 == 0 && a.D <= NM_MAXV_LIMIT * 128, "norm_modulate: hidden size must be a multiple of 4 and <= 2048");
   VV_CHECK(a.mod_ld % 4 == 0 && a.scale_off % 4 == 0 && (a.shift_off < 0 || a.shift_off % 4 == 0) && a.ldo % 4 == 0,
            "norm_modulate: alignment");
   int grid = cdiv(a.M, 8);
-  if (a.out_bf16)
-    k_norm_modulate<true><<<grid, 256, 0, s>>>(a);
-  else
-    k_norm_modulate<false><<<grid, 256, 0, s>>>(a);
+  const int nv = cdiv(a.D / 4, 32);  // float4 per lane
+#define VV_NM_LAUNCH(BF, MV) k_norm_modulate<BF, MV><<<grid, 256, 0, s>>>(a)
+  if (a.out_bf16) {
+    if (nv <= 4) VV_NM_LAUNCH(true, 4);
+    else if (nv <= 6) VV_NM_LAUNCH(true, 6);
+    else if (nv <= 9) VV_NM_LAUNCH(true, 9);
+    else if (nv <= 12) VV_NM_LAUNCH(true, 12);
+    else VV_NM_LAUNCH(true, 16);
+  } else {
+    if (nv <= 4) VV_NM_LAUNCH(false, 4);
+    else if (nv <= 9) VV_NM_LAUNCH(false, 9);
+    else VV_NM_LAUNCH(false, 16);
+  }
+#undef VV_NM_LAUNCH
   VV_LAUNCH_CHECK();
 }
 
