@@ -125,6 +125,203 @@ __device__ __noinline__ void qk_head_stats(uint32_t tbase, int hc0, int n0, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ fast epilogue
+// Guard-free epilogue for the production cases: interior tile (all 128 rows < M, all BN columns < N), 32-column
+// chunks, the warp's 32 rows are consecutive tokens of one sample (T % 32 == 0), QKV without qk-norm.  Same math
+// as the generic path below; every bound check, per-pass division and generic-address store is gone (the generic
+// path measured ~900 instructions per 32x32 chunk, mostly integer address/guard code).
+__device__ __forceinline__ void sts128(uint32_t addr, float a0, float a1, float a2, float a3) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int EPI>
+__device__ __forceinline__ bool epi_fast_supported(const TcGemmArgs& a) {
+  if (EPI == TC_EPI_GATED_RESIDUAL || EPI == TC_EPI_SWIGLU) return true;
+  if (EPI == TC_EPI_QKV) return a.qn_w == nullptr && a.kn_w == nullptr;
+  return false;
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_t st_s, const uint32_t tbase,
+                                              uint64_t* tfull, const uint32_t aphase, const int m0, const int n0,
+                                              const int n_blk, const int BN, const int q, const int half,
+                                              const int lane) {
+  constexpr int CW = 32, LPR = 8, RPP = 4, SST = (CW + 4) * 4;  // staging row stride in bytes
+  const int prow = lane >> 3, pcc = (lane & 7) * 4;
+  const int wrow0 = m0 + q * 32;
+  const int wb = wrow0 / a.T, wt0 = wrow0 - wb * a.T;
+  const int n_chunks = BN / CW;
+  const uint32_t st_w = st_s + (uint32_t)lane * SST;            // thread == row staging write base
+  const uint32_t st_r = st_s + (uint32_t)prow * SST + pcc * 4;  // row-pass read base (+ ps * RPP * SST)
+  const bool fusedc = (EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU) && a.in_part != nullptr;
+
+  // ---- tile prologue (before the accumulator is ready)
+  float in_rstd = 1.f;
+  const float* bvec = a.bias;
+  if (fusedc) {
+    float ssum = 0.f;
+    for (int pi = 0; pi < a.in_nparts; ++pi) ssum += a.in_part[(size_t)pi * a.M + wrow0 + lane];
+    in_rstd = rsqrtf(ssum / (float)a.in_dim + 1e-6f);
+    bvec = a.sp + (size_t)wb * a.sp_ld;
+  }
+  const float* modrow = a.mod + (size_t)wb * a.mod_ld;
+  float* xptr = nullptr;   // this lane's first residual element of chunk 0, pass 0
+  bf16* nxptr = nullptr;
+  if (EPI == TC_EPI_GATED_RESIDUAL) {
+    xptr = reinterpret_cast<float*>(a.out) + (size_t)(wrow0 + prow) * a.ldo + n0 + pcc;
+    if (a.nx_w) nxptr = a.nx_A + (size_t)(wrow0 + prow) * a.ldo + n0 + pcc;
+  }
+  const size_t xpass = (size_t)RPP * a.ldo;  // elements between passes
+  float4 xpre[LPR];
+  float4 bb_n = make_float4(0.f, 0.f, 0.f, 0.f), g_n = bb_n, cw_n = bb_n;
+  auto prefetch = [&](int c) {
+    if (c >= n_chunks) return;
+    const int colv = n0 + c * CW + pcc;
+    if (bvec) bb_n = *reinterpret_cast<const float4*>(bvec + colv);
+    if (EPI == TC_EPI_GATED_RESIDUAL) {
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) xpre[ps] = *reinterpret_cast<const float4*>(xptr + ps * xpass + c * CW);
+      g_n = *reinterpret_cast<const float4*>(modrow + a.gate_off + colv);
+      if (a.nx_w) {
+        const float4 w4 = *reinterpret_cast<const float4*>(a.nx_w + colv);
+        const float4 s4 = *reinterpret_cast<const float4*>(modrow + a.nx_scale_off + colv);
+        cw_n = make_float4(w4.x * (1.f + s4.x), w4.y * (1.f + s4.y), w4.z * (1.f + s4.z), w4.w * (1.f + s4.w));
+      }
+    }
+  };
+  prefetch(half);
+  float ssacc[LPR];
+#pragma unroll
+  for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
+
+  ptx::mbar_wait(tfull, aphase);
+  ptx::tc_fence_after();
+
+  for (int c = half; c < n_chunks; c += 2) {
+    const int c0 = c * CW;
+    uint32_t r[CW];
+    ptx::tmem_ld_x32(tbase + c0, r);
+    float4 xcur[LPR];
+    if (EPI == TC_EPI_GATED_RESIDUAL) {
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) xcur[ps] = xpre[ps];
+    }
+    const float4 bb = bb_n, g1 = g_n, cw = cw_n;
+    prefetch(c + 2);
+    ptx::tmem_ld_wait();
+
+    // stage the 32 x 32 fp32 block (thread == row), scaled by 1/rms when the norm is fused
+    __syncwarp();
+#pragma unroll
+    for (int j4 = 0; j4 < CW / 4; ++j4)
+      sts128(st_w + j4 * 16, __uint_as_float(r[j4 * 4]) * in_rstd, __uint_as_float(r[j4 * 4 + 1]) * in_rstd,
+             __uint_as_float(r[j4 * 4 + 2]) * in_rstd, __uint_as_float(r[j4 * 4 + 3]) * in_rstd);
+    __syncwarp();
+
+    if (EPI == TC_EPI_GATED_RESIDUAL) {
+      float* xo = xptr + c0;
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) {
+        const float4 v = lds128(st_r + ps * RPP * SST);
+        float4 x = xcur[ps];
+        x.x = fmaf(g1.x, v.x + bb.x, x.x); x.y = fmaf(g1.y, v.y + bb.y, x.y);
+        x.z = fmaf(g1.z, v.z + bb.z, x.z); x.w = fmaf(g1.w, v.w + bb.w, x.w);
+        *reinterpret_cast<float4*>(xo + ps * xpass) = x;
+        if (a.nx_w) {
+          ssacc[ps] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+          *reinterpret_cast<uint2*>(nxptr + c0 + ps * xpass) =
+              make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
+        }
+      }
+    } else if (EPI == TC_EPI_SWIGLU) {
+      bf16* ho = reinterpret_cast<bf16*>(a.out) + (size_t)(wrow0 + prow) * a.ldo + ((n0 + c0 + pcc) >> 1);
+      const size_t hpass = (size_t)RPP * a.ldo;
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) {
+        float4 v = lds128(st_r + ps * RPP * SST);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        *reinterpret_cast<uint32_t*>(ho + ps * hpass) = pack_bf16(silu_fast(v.x) * v.y, silu_fast(v.z) * v.w);
+      }
+    } else if (EPI == TC_EPI_QKV) {
+      const int D = a.H * a.hd;
+      const int colc = n0 + c0;
+      const int which = colc / D;  // chunk-uniform: D % 32 == 0
+      if (which == 2) {
+        // V^T: lane owns head-dim column j and 8 consecutive tokens -> one 16-byte store of (B,H,hdv,T)
+        const int tg = lane & 3;
+        float bv4[4];
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) bv4[ps] = bvec[colc + ps * 8 + (lane >> 2)];
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const int j = ps * 8 + (lane >> 2);
+          const int rem = colc + j - 2 * D, h = rem / a.hd, d = rem - h * a.hd;
+          const uint32_t sa = st_s + (uint32_t)(tg * 8) * SST + j * 4;
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = lds32(sa + e * SST) + bv4[ps];
+          *reinterpret_cast<uint4*>(a.vt + (((size_t)wb * a.H + h) * a.hdv + d) * a.T + wt0 + tg * 8) =
+              make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        }
+      } else {
+        // q / k: bias, RoPE (pos_embed.py:38-42,135), head-major store; all table loads before the first store
+        const int rem = colc + pcc - which * D, h = rem / a.hd, d = rem - h * a.hd;
+        bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)wb * a.H + h) * a.T + wt0 + prow) * a.hdp + d;
+        const size_t dpass = (size_t)RPP * a.hdp;
+        const float* cp = a.cos ? a.cos + (size_t)(wt0 + prow) * a.hd + d : nullptr;
+        const float* sp_ = a.cos ? a.sin + (size_t)(wt0 + prow) * a.hd + d : nullptr;
+        const size_t tpass = (size_t)RPP * a.hd;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {  // two batches of four passes keep the register count in check
+          float4 c4[4], s4[4];
+          if (a.cos) {
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+              c4[pp] = *reinterpret_cast<const float4*>(cp + (hf * 4 + pp) * tpass);
+              s4[pp] = *reinterpret_cast<const float4*>(sp_ + (hf * 4 + pp) * tpass);
+            }
+          }
+#pragma unroll
+          for (int pp = 0; pp < 4; ++pp) {
+            const int ps = hf * 4 + pp;
+            float4 v = lds128(st_r + ps * RPP * SST);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            if (a.cos) {
+              float4 o;
+              o.x = v.x * c4[pp].x - v.y * s4[pp].x;
+              o.y = v.y * c4[pp].y + v.x * s4[pp].y;
+              o.z = v.z * c4[pp].z - v.w * s4[pp].z;
+              o.w = v.w * c4[pp].w + v.z * s4[pp].w;
+              v = o;
+            }
+            *reinterpret_cast<uint2*>(dst + ps * dpass) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+          }
+        }
+      }
+    }
+  }
+  if (EPI == TC_EPI_GATED_RESIDUAL && a.nx_w) {
+#pragma unroll
+    for (int ps = 0; ps < LPR; ++ps) {
+      float v = ssacc[ps];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if ((lane & 7) == 0) a.nx_part[(size_t)(n_blk * 2 + half) * a.M + wrow0 + ps * RPP + prow] = v;
+    }
+  }
+}
+
 struct TcSmemBars {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
@@ -231,11 +428,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int prow = lane / LPR;   // row (within a pass) and column group this lane owns in the row-wise pass
     const int pcc = (lane % LPR) * 4;
     const bool rows_one_sample = (a.T % 32) == 0;  // the warp's 32 rows are consecutive tokens of one sample
+    const bool fast_ok = rows_one_sample && (BN % 32 == 0) && epi_fast_supported<EPI>(a) &&
+                         (EPI != TC_EPI_QKV || ((a.H * a.hd) % 32 == 0 && a.hd % 4 == 0));
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int m0 = m_blk * TC_BM, n0 = n_blk * BN;
+      if (CW == 32 && fast_ok && m0 + TC_BM <= a.M && n0 + BN <= a.N) {
+        // interior tile of a production epilogue: guard-free path
+        epi_tile_fast<EPI>(a, ptx::smem_u32(st), tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256,
+                           &bars->tfull[as], aphase, m0, n0, n_blk, BN, q, half, lane);
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars->tempty[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+        continue;
+      }
       const int wrow0 = m0 + q * 32;     // first row of this warp
       const int my_row = wrow0 + lane;   // thread == row domain
       const int wb = wrow0 / a.T, wt0 = wrow0 - wb * a.T;  // sample / first token of the warp (valid if rows_one_sample)
