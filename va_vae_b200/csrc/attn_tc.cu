@@ -48,6 +48,33 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// tcgen05.wait::ld that also names the destination registers as in/out operands, so the compiler cannot schedule
+// arithmetic on registers of an in-flight tcgen05.ld above the wait (needed once loads are software-pipelined).
+__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 // K-major operand tile whose rows are 32 bytes (16 bf16) with the 32-byte swizzle (CU_TENSOR_MAP_SWIZZLE_32B):
 // 8-row groups are 256 bytes apart; layout type 6.
 __device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t smem_addr) {
@@ -229,6 +256,49 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const bool ragged = (kvlen & 15) != 0;  // only the last 16-column group can hold invalid keys
         ptx::mbar_wait(&bars->s_full, ph);
         ptx::tc_fence_after();
+        float m_new, alpha, moff;
+        if (n_s == AT_BKV && !ragged) {
+          // ---- full 256-key block: fully unrolled, TMEM loads software-pipelined (load chunk i+1 while reducing /
+          //      exponentiating chunk i; two 32-register buffers)
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_x32(trow, ra);
+          tmem_ld_wait_dep32(ra);
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t* cur = (i & 1) ? rb : ra;
+            uint32_t* nxt = (i & 1) ? ra : rb;
+            ptx::tmem_ld_x32(trow + (uint32_t)(((i + 1) & 7) * 32), nxt);  // i == 7 prefetches chunk 0 for pass 2
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              m4[0] = fmaxf(m4[0], __uint_as_float(cur[j]));
+              m4[1] = fmaxf(m4[1], __uint_as_float(cur[j + 1]));
+              m4[2] = fmaxf(m4[2], __uint_as_float(cur[j + 2]));
+              m4[3] = fmaxf(m4[3], __uint_as_float(cur[j + 3]));
+            }
+            tmem_ld_wait_dep32(nxt);
+          }
+          const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          m_new = fmaxf(m_run, mx);
+          alpha = exp2f((m_run - m_new) * sl2);  // 0 on the first block (m_run = -inf)
+          moff = m_new * sl2;
+          // pass 2: chunk 0 is already in `ra`.  P (16 packed columns per 32 keys) is written behind the read
+          // front: chunk i+1 (columns 32(i+1)..) has been read into registers before P of chunk i lands on
+          // columns 16i..16i+15.
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t* cur = (i & 1) ? rb : ra;
+            uint32_t* nxt = (i & 1) ? ra : rb;
+            if (i < 7) ptx::tmem_ld_x32(trow + (uint32_t)((i + 1) * 32), nxt);
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)
+              pk[j >> 1] = ex2_bf16x2(fmaf(__uint_as_float(cur[j]), sl2, -moff), fmaf(__uint_as_float(cur[j + 1]), sl2, -moff));
+            if (i < 7) tmem_ld_wait_dep32(nxt);   // the next chunk is in registers before P overwrites its S columns
+            tmem_st_x16(trow + (uint32_t)(i * 16), pk);
+          }
+        } else {
+        // ---- generic block (fewer than 256 keys and / or a ragged tail)
         // pass 1: row maximum
         float mx = -INFINITY;
         for (int c0 = 0; c0 < n_s; c0 += 32) {
@@ -256,10 +326,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         }
-        const float m_new = fmaxf(m_run, mx);
-        const float alpha = exp2f((m_run - m_new) * sl2);  // 0 on the first block (m_run = -inf)
-        const float moff = m_new * sl2;
-        m_run = m_new;
+        m_new = fmaxf(m_run, mx);
+        alpha = exp2f((m_run - m_new) * sl2);  // 0 on the first block (m_run = -inf)
+        moff = m_new * sl2;
         // pass 2: p = 2^(s*scale*log2e - m) as packed bf16 pairs, written back to TMEM (16 keys -> 8 columns;
         // the write front at c0/2 never passes the read front at c0, so S is not clobbered before it is read)
         for (int c0 = 0; c0 < n_s; c0 += 16) {
@@ -279,6 +348,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           tmem_st_x8(trow + (uint32_t)(c0 >> 1), pk);
         }
+        }
+        m_run = m_new;
         tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&bars->p_full);
