@@ -359,42 +359,58 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         ptx::tc_fence_after();
         const bool last = blk == nblk - 1;
         if (!MULTI) {
-          // single block: normalise and store straight from TMEM
-          uint32_t rl[16];
-          ptx::tmem_ld_x16(trow + O_COL + (uint32_t)((a.hd >> 4) << 4), rl);  // the 16-column group holding column hd
-          ptx::tmem_ld_wait();
-          float l = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j == (a.hd & 15)) l = __uint_as_float(rl[j]);
-          const float inv = 1.0f / l;
+          // single block: normalise and store straight from TMEM.  All O columns (and the row-sum column hd) are
+          // requested first and waited for once; TMEM is released before the global stores.
           const int b = bh / a.H, h = bh % a.H;
           const bool valid = (q0 + row) < a.T;
           bf16* orow = a.out + ((size_t)b * a.T + q0 + row) * ((size_t)a.H * a.hd) + (size_t)h * a.hd;
-          for (int c0 = 0; c0 < a.hd; c0 += 16) {
-            uint32_t r[16];
-            ptx::tmem_ld_x16(trow + O_COL + c0, r);
-            ptx::tmem_ld_wait();
-            if (valid) {
+          const int ncol = ((a.hd >> 4) + 1) << 4;   // 16-column groups up to and including the one holding column hd
+          auto store8 = [&](const uint32_t* r8, int c, float inv) {   // 8 consecutive columns -> one 16-byte store
+            if (!valid || c >= a.hd) return;
+            uint4 pk;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r8[0]) * inv, __uint_as_float(r8[1]) * inv);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r8[2]) * inv, __uint_as_float(r8[3]) * inv);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r8[4]) * inv, __uint_as_float(r8[5]) * inv);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r8[6]) * inv, __uint_as_float(r8[7]) * inv);
+            pk.x = *reinterpret_cast<uint32_t*>(&t0);
+            pk.y = *reinterpret_cast<uint32_t*>(&t1);
+            pk.z = *reinterpret_cast<uint32_t*>(&t2);
+            pk.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(orow + c) = pk;
+          };
+          if (ncol == 80) {
+            // head_dim 64 / 72 (every registry model): 80 columns in three loads, one wait, TMEM released early
+            uint32_t o0[32], o1[32], o2[16];
+            ptx::tmem_ld_x32(trow + O_COL, o0);
+            ptx::tmem_ld_x32(trow + O_COL + 32, o1);
+            ptx::tmem_ld_x16(trow + O_COL + 64, o2);
+            tmem_ld_wait_dep32(o0);
+            tmem_ld_wait_dep32(o1);
+            tmem_ld_wait_dep16(o2);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&bars->o_empty);   // O / P columns may be overwritten by the next S MMA from here on
+            const float inv = 1.0f / __uint_as_float(a.hd == 64 ? o2[0] : o2[8]);   // column hd holds the row sum
 #pragma unroll
-              for (int j8 = 0; j8 < 2; ++j8) {
-                if (c0 + j8 * 8 < a.hd) {  // hd % 8 == 0
-                  uint4 pk;
-                  __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 0]) * inv, __uint_as_float(r[j8 * 8 + 1]) * inv);
-                  __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 2]) * inv, __uint_as_float(r[j8 * 8 + 3]) * inv);
-                  __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 4]) * inv, __uint_as_float(r[j8 * 8 + 5]) * inv);
-                  __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 6]) * inv, __uint_as_float(r[j8 * 8 + 7]) * inv);
-                  pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                  pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                  pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                  *reinterpret_cast<uint4*>(orow + c0 + j8 * 8) = pk;
-                }
-              }
+            for (int j = 0; j < 4; ++j) {
+              store8(o0 + j * 8, j * 8, inv);
+              store8(o1 + j * 8, 32 + j * 8, inv);
             }
+            store8(o2, 64, inv);
+          } else {
+            uint32_t rl[16];
+            ptx::tmem_ld_x16(trow + O_COL + (uint32_t)((a.hd >> 4) << 4), rl);  // the 16-column group holding column hd
+            tmem_ld_wait_dep16(rl);
+            const float inv = 1.0f / __uint_as_float((a.hd & 15) ? rl[8] : rl[0]);
+            for (int c0 = 0; c0 < a.hd; c0 += 16) {
+              uint32_t r[16];
+              ptx::tmem_ld_x16(trow + O_COL + c0, r);
+              tmem_ld_wait_dep16(r);
+              store8(r, c0, inv);
+              store8(r + 8, c0 + 8, inv);
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&bars->o_empty);
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&bars->o_empty);
         } else {
           // online softmax: rescale the running O (and running row sum in column hd) and add this block
           for (int c0 = 0; c0 < ncol_o; c0 += 16) {
