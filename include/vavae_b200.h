@@ -129,6 +129,9 @@ int vavae_test_gemm_bf16(const void* A, const void* W, const float* bias, float*
  * (see DESIGN.md "attention layouts"). */
 int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int T, int hd,
                               void* stream);
+/* 1: GEMMs use the CTA-pair kernel (cluster of 2, tcgen05 cta_group::2, M = 256 per pair) where the problem
+ * allows it; 0: always the single-CTA kernel.  Process-wide; default set by the engine. */
+int vavae_set_gemm_two_cta(int on);
 /* Per-kernel timing: runs the named kernel of the engine's own layer 0 `iters` times on the given
  * number of model rows with CUDA events on `stream`; returns mean milliseconds per launch in *ms. */
 int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work,

@@ -20,15 +20,20 @@ def _dev():
     (128, 128, 64), (128, 256, 128), (256, 384, 1152), (1000, 3456, 1152), (6, 512, 384), (256, 200, 128),
     (128, 128, 200), (4096, 1152, 3072), (300, 64, 2736), (128, 32, 64), (128, 16, 128), (16384, 6144, 1152),
 ])
-def test_tcgen05_gemm_matches_fp32_matmul(M, N, K):
+@pytest.mark.parametrize("two_cta", [True, False])
+def test_tcgen05_gemm_matches_fp32_matmul(M, N, K, two_cta):
+    """two_cta=True: CTA-pair kernel (cluster of 2, tcgen05 cta_group::2, M = 256 per pair) where M >= 256;
+    False: single-CTA kernel."""
     from va_vae_b200 import engine as E
     dev = _dev()
+    E.set_gemm_two_cta(two_cta)
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
     A = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16().contiguous()
     W = (torch.randn(N, K, generator=g) * 0.5).to(dev).bfloat16().contiguous()
     bias = torch.randn(N, generator=g).to(dev)
     out = E.test_gemm_bf16(A, W, bias)
     torch.cuda.synchronize()
+    E.set_gemm_two_cta(True)
     ref = A.float() @ W.float().t() + bias
     err = rel_l2(out, ref)
     assert err < 2e-5, f"tcgen05 GEMM {M}x{N}x{K}: rel-L2 {err:.3e}"    # same bf16 inputs, fp32 accumulate

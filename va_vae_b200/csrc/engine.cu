@@ -940,6 +940,11 @@ int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void
   }
 }
 
+int vavae_set_gemm_two_cta(int on) {
+  vv::set_gemm_two_cta(on);
+  return 0;
+}
+
 int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work, void* stream) {
   VV_API_BEGIN(e)
   VV_CHECK(e && e->finalized && kernel && ms && work, "bad argument");

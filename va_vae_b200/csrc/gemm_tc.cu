@@ -330,18 +330,89 @@ struct TcSmemBars {
   uint32_t tmem_base;
 };
 
-template <int EPI, int CW>
+// ------------------------------------------------------------------------------------------------ 2-CTA (cta_group::2)
+namespace ptx2 {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  const uint32_t bar_leader = ptx::smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (128 rows per CTA) * B^T (N/2 rows per CTA); issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the leader's prior MMAs retire) on the same-offset mbarrier of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(ptx::smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+}  // namespace ptx2
+
+// TWO = true: CTA pairs (cluster of 2, cta_group::2).  A pair computes a 256 x BN tile: each CTA loads its own 128
+// rows of A and HALF of the W tile (BN/2 rows); the leader's single thread issues M=256 MMAs that read both CTAs'
+// shared memory and write each CTA's 128 x BN accumulator into its own TMEM.  Per flop this halves the W-tile
+// shared-memory fill and L2 traffic, which is what limits (and powers) the 1-CTA kernel.
+template <int EPI, int CW, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
           const int BN, const int nstages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int stage_bytes = TC_A_BYTES + BN * 128;
+  const int b_rows = TWO ? BN / 2 : BN;                 // W-tile rows this CTA loads
+  const int stage_bytes = TC_A_BYTES + b_rows * 128;
+  const uint32_t rank = TWO ? ptx2::cluster_ctarank() : 0u;   // 0 = leader
+  const int tile_m = TWO ? 2 * TC_BM : TC_BM;           // rows per scheduled tile
+  const int sched_id = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int sched_n = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   float* staging = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
   TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(reinterpret_cast<uint8_t*>(staging) + 8 * 32 * (CW + 4) * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (a.M + TC_BM - 1) / TC_BM;
+  const int m_tiles = (a.M + tile_m - 1) / tile_m;
   const int n_tiles = (a.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (a.K + TC_BK - 1) / TC_BK;
@@ -355,16 +426,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->tfull[i], 1);
-      ptx::mbar_init(&bars->tempty[i], 256);
+      ptx::mbar_init(&bars->tempty[i], TWO ? 512 : 256);   // 2-CTA: both CTAs' epilogue threads release the leader
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&bars->tmem_base, 512);
-    ptx::tmem_relinquish();
+    if (TWO) {
+      ptx2::tmem_alloc2(&bars->tmem_base, 512);
+      ptx2::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(&bars->tmem_base, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (TWO) ptx2::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -373,28 +449,35 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + TC_A_BYTES;
-          ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
-          ptx::tma_load_2d(sa, &tmA, &bars->full[stage], kb * TC_BK, m_blk * TC_BM);
-          ptx::tma_load_2d(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN);
+          if (TWO) {
+            // both CTAs' bytes are credited to the leader's barrier; only the leader arms it (with the pair's total)
+            if (rank == 0) ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * stage_bytes));
+            ptx2::tma_load_2d_2sm(sa, &tmA, &bars->full[stage], kb * TC_BK, m_blk * tile_m + (int)rank * TC_BM);
+            ptx2::tma_load_2d_2sm(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN + (int)rank * b_rows);
+          } else {
+            ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+            ptx::tma_load_2d(sa, &tmA, &bars->full[stage], kb * TC_BK, m_blk * TC_BM);
+            ptx::tma_load_2d(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN);
+          }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(TC_BM, BN);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(tile_m, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         ptx::mbar_wait(&bars->tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)as * 256;
@@ -407,13 +490,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr>>4) field
-            ptx::umma_bf16_ss(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                              (uint32_t)((kb | k) != 0));
+            if (TWO)
+              ptx2::umma_bf16_ss_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                     (uint32_t)((kb | k) != 0));
+            else
+              ptx::umma_bf16_ss(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                (uint32_t)((kb | k) != 0));
           }
-          ptx::umma_commit(&bars->empty[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (TWO) ptx2::umma_commit_mc(&bars->empty[stage], 3); else ptx::umma_commit(&bars->empty[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&bars->tfull[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (TWO) ptx2::umma_commit_mc(&bars->tfull[as], 3); else ptx::umma_commit(&bars->tfull[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -432,15 +521,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                          (EPI != TC_EPI_QKV || ((a.H * a.hd) % 32 == 0 && a.hd % 4 == 0));
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // releases an accumulator stage to the MMA-issuing thread (which lives in the leader CTA of a pair)
+    auto release_acc = [&](int stage_idx) {
+      ptx::tc_fence_before();
+      if (TWO && rank != 0) ptx2::mbar_arrive_remote(&bars->tempty[stage_idx], 0);
+      else ptx::mbar_arrive(&bars->tempty[stage_idx]);
+    };
+    for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int m0 = m_blk * TC_BM, n0 = n_blk * BN;
+      const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
       if (CW == 32 && fast_ok && m0 + TC_BM <= a.M && n0 + BN <= a.N) {
         // interior tile of a production epilogue: guard-free path
         epi_tile_fast<EPI>(a, ptx::smem_u32(st), tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256,
                            &bars->tfull[as], aphase, m0, n0, n_blk, BN, q, half, lane);
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&bars->tempty[as]);
+        release_acc(as);
         as ^= 1;
         if (as == 0) aphase ^= 1;
         continue;
@@ -737,18 +831,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }
       // release this accumulator stage to the MMA warp
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bars->tempty[as]);
+      release_acc(as);
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (TWO) ptx2::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (TWO) ptx2::tmem_dealloc2(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -796,9 +889,14 @@ int gemm_tc_pick_bn(const TcGemmArgs& a) {
   return best;
 }
 
-template <int EPI, int CW>
-static void launch_inst(const TcGemmArgs& a, int BN, cudaStream_t s) {
-  const int stage_bytes = TC_A_BYTES + BN * 128;
+static int g_two_cta = 1;   // 1 (default): CTA-pair kernel where the problem allows it, 0: always the 1-CTA kernel
+void set_gemm_two_cta(int on) { g_two_cta = on; }
+int get_gemm_two_cta() { return g_two_cta; }
+
+template <int EPI, int CW, bool TWO>
+static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
+  const int b_rows = TWO ? BN / 2 : BN;
+  const int stage_bytes = TC_A_BYTES + b_rows * 128;
   const int fixed = 8 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024;
   int nstages = (227 * 1024 - fixed) / stage_bytes;
   if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
@@ -806,15 +904,41 @@ static void launch_inst(const TcGemmArgs& a, int BN, cudaStream_t s) {
   const size_t smem = (size_t)nstages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    VV_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VV_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, CW, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   CUtensorMap tmA = make_tmap_2d_bf16(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, TC_BK, TC_BM);
-  CUtensorMap tmB = make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK, (uint32_t)BN);
-  const int tiles = cdiv(a.M, TC_BM) * cdiv(a.N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  k_gemm_tc<EPI, CW><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a, BN, nstages);
+  CUtensorMap tmB = make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK, (uint32_t)b_rows);
+  if (!TWO) {
+    const int tiles = cdiv(a.M, TC_BM) * cdiv(a.N, BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    k_gemm_tc<EPI, CW, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a, BN, nstages);
+  } else {
+    const int tiles = cdiv(a.M, 2 * TC_BM) * cdiv(a.N, BN);
+    const int pairs = std::min(tiles, num_sms() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, true>, tmA, tmB, a, BN, nstages));
+  }
   VV_LAUNCH_CHECK();
+}
+
+template <int EPI, int CW>
+static void launch_inst(const TcGemmArgs& a, int BN, cudaStream_t s) {
+  // CTA pairs need two full 128-row halves worth of work and a W tile that splits into 8-row-aligned halves
+  const bool two = g_two_cta && a.M >= 2 * TC_BM && (BN % 16 == 0) && BN >= 32;
+  if (two) launch_inst2<EPI, CW, true>(a, BN, s);
+  else launch_inst2<EPI, CW, false>(a, BN, s);
 }
 
 template <int EPI>

@@ -54,6 +54,9 @@ struct TcGemmArgs {
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
 int gemm_tc_pick_bn(const TcGemmArgs& a);
+// 1: use the CTA-pair (cta_group::2) kernel where the problem allows it; 0: always the 1-CTA kernel
+void set_gemm_two_cta(int on);
+int get_gemm_two_cta();
 
 struct TcAttnArgs {
   const bf16 *q, *k;  // (B,H,T,hdp)

@@ -23,7 +23,7 @@ EXPORTS = [
     "vavae_abi_version", "vavae_last_error", "vavae_create", "vavae_destroy", "vavae_load_weight", "vavae_finalize",
     "vavae_forward", "vavae_forward_with_cfg", "vavae_sample_ode", "vavae_sample_ode_host", "vavae_launch_count",
     "vavae_device_bytes", "vavae_test_gemm_bf16", "vavae_test_attention_bf16", "vavae_time_kernel",
-    "vavae_profile_begin", "vavae_profile_end",
+    "vavae_profile_begin", "vavae_profile_end", "vavae_set_gemm_two_cta",
 ]
 
 
@@ -69,6 +69,7 @@ def load_library() -> ctypes.CDLL:
     lib.vavae_test_attention_bf16.argtypes = [c_void, c_void, c_void, c_void, c_int, c_int, c_int, c_int, c_void]
     lib.vavae_time_kernel.argtypes = [c_void, ctypes.c_char_p, c_int, c_int, ctypes.POINTER(c_float),
                                       ctypes.POINTER(ctypes.c_double), c_void]
+    lib.vavae_set_gemm_two_cta.argtypes = [c_int]
     lib.vavae_profile_begin.argtypes = [c_void, ctypes.c_char_p]
     lib.vavae_profile_end.argtypes = [c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_double)]
@@ -239,6 +240,11 @@ class Engine:
     def _check_x(self, x):
         if x.dim() != 4 or x.shape[1] != self.C or x.shape[2] != self.img or x.shape[3] != self.img:
             raise ValueError(f"expected x of shape (N, {self.C}, {self.img}, {self.img}), got {tuple(x.shape)}")
+
+
+def set_gemm_two_cta(on: bool):
+    """Process-wide switch between the single-CTA and the CTA-pair (cta_group::2) GEMM kernels."""
+    load_library().vavae_set_gemm_two_cta(1 if on else 0)
 
 
 def test_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
