@@ -856,6 +856,23 @@ static int num_sms() {
   return g_num_sms;
 }
 
+// 0: always the 1-CTA kernel; 1: CTA pairs only for the GEMMs whose main loop dominates (w12, w3, large-K QKV);
+// 2 (default): CTA pairs wherever the shape allows it.  Measured on B200, whole 250-step sampler, power-capped
+// (profiles/r1_two_cta_ab.md): B/1 741 / 771 / 785 TFLOP/s and XL/1 851 / 919 / 928 TFLOP/s for modes 0 / 1 / 2 --
+// in isolation proj and the small-K QKV lose a few % with pairs, but under the 1 kW cap the halved W-tile
+// traffic buys clock.
+static int g_two_cta = 2;
+static bool want_two_cta(const TcGemmArgs& a) {
+  if (g_two_cta == 0 || a.M < 2 * TC_BM) return false;
+  if (g_two_cta >= 2) return true;
+  switch (a.epi) {
+    case TC_EPI_SWIGLU:
+    case TC_EPI_GELU_BF16: return true;
+    case TC_EPI_GATED_RESIDUAL: return a.K >= 2 * a.N;
+    case TC_EPI_QKV: return a.K >= 1024;
+    default: return false;
+  }
+}
 int gemm_tc_pick_bn(const TcGemmArgs& a) {
   if (a.epi == TC_EPI_FINAL) {
     int bn = ((a.N + 15) / 16) * 16;
@@ -870,6 +887,7 @@ int gemm_tc_pick_bn(const TcGemmArgs& a) {
     VV_CHECK(best > 0, "qk-norm epilogue: no tile width <= 256 holds whole heads (head_dim must divide a multiple of 16)");
     return best;
   }
+  if (want_two_cta(a) && a.N % 256 == 0 && !(a.epi == TC_EPI_QKV && a.qn_w)) return 256;
   const int cands[3] = {256, 192, 128};
   int best = 128;
   double best_eff = -1.0;
@@ -889,7 +907,6 @@ int gemm_tc_pick_bn(const TcGemmArgs& a) {
   return best;
 }
 
-static int g_two_cta = 1;   // 1 (default): CTA-pair kernel where the problem allows it, 0: always the 1-CTA kernel
 void set_gemm_two_cta(int on) { g_two_cta = on; }
 int get_gemm_two_cta() { return g_two_cta; }
 
@@ -936,7 +953,7 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
 template <int EPI, int CW>
 static void launch_inst(const TcGemmArgs& a, int BN, cudaStream_t s) {
   // CTA pairs need two full 128-row halves worth of work and a W tile that splits into 8-row-aligned halves
-  const bool two = g_two_cta && a.M >= 2 * TC_BM && (BN % 16 == 0) && BN >= 32;
+  const bool two = want_two_cta(a) && (BN % 16 == 0) && BN >= 32;
   if (two) launch_inst2<EPI, CW, true>(a, BN, s);
   else launch_inst2<EPI, CW, false>(a, BN, s);
 }

@@ -73,6 +73,8 @@ def load_library() -> ctypes.CDLL:
     lib.vavae_profile_begin.argtypes = [c_void, ctypes.c_char_p]
     lib.vavae_profile_end.argtypes = [c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_double)]
+    if "VAVAE_GEMM_2CTA" in os.environ:      # 0 = never, 1 = main-loop-bound GEMMs only, 2 = wherever possible (default)
+        lib.vavae_set_gemm_two_cta(int(os.environ["VAVAE_GEMM_2CTA"]))
     if lib.vavae_abi_version() != ABI_VERSION:
         raise RuntimeError("libvavae_b200.so ABI version mismatch; rebuild with python -m va_vae_b200.build --force")
     _lib = lib
@@ -244,7 +246,7 @@ class Engine:
 
 def set_gemm_two_cta(on: bool):
     """Process-wide switch between the single-CTA and the CTA-pair (cta_group::2) GEMM kernels."""
-    load_library().vavae_set_gemm_two_cta(1 if on else 0)
+    load_library().vavae_set_gemm_two_cta(int(on) if not isinstance(on, bool) else (2 if on else 0))
 
 
 def test_gemm_bf16(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
