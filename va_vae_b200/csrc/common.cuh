@@ -89,6 +89,8 @@ struct EmbedArgs {
 };
 void launch_patch_embed(const EmbedArgs& a, cudaStream_t s);
 
+void launch_cond_combine(const float* temb, const float* table, const int64_t* labels, RowMap rm, float* sc_f, bf16* sc_h,
+                         int rows, int D, cudaStream_t s);
 void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowMap rm, cudaStream_t s);
 
 struct NormModArgs {

@@ -475,6 +475,19 @@ static TcGemmArgs tc_args(const bf16* A, int lda, const bf16* Wt, int ldw, int M
 
 static void conditioning(vavae_engine* e, int rows, const RowMap& rm, const float* t, const int64_t* y, cudaStream_t s) {
   const int D = e->D;
+  if (rm.t_stride == 0) {
+    // the sampler's case: one timestep for the whole batch -> run the timestep MLP on a single row
+    RowMap r1 = rm;
+    r1.seg_rows = 1;
+    r1.t_off[0] = r1.t_off[1] = 0;
+    launch_tfreq(t, e->W("t_embedder.freqs").d, e->tf, 1, r1, s);
+    gemm32(e->tf, 256, e->W("t_embedder.mlp.0.weight").d, e->W("t_embedder.mlp.0.bias").d, e->th, D, 1, D, 256,
+           F32_EPI_SILU, s);
+    gemm32(e->th, D, e->W("t_embedder.mlp.2.weight").d, e->W("t_embedder.mlp.2.bias").d, e->cbuf, D, 1, D, D,
+           F32_EPI_NONE, s);
+    launch_cond_combine(e->cbuf, e->W("y_embedder.embedding_table.weight").d, y, rm, e->fp32 ? e->sc_f : nullptr,
+                        e->fp32 ? nullptr : e->sc_h, rows, D, s);
+  } else {
   launch_tfreq(t, e->W("t_embedder.freqs").d, e->tf, rows, rm, s);
   gemm32(e->tf, 256, e->W("t_embedder.mlp.0.weight").d, e->W("t_embedder.mlp.0.bias").d, e->th, D, rows, D, 256,
          F32_EPI_SILU, s);
@@ -485,6 +498,7 @@ static void conditioning(vavae_engine* e, int rows, const RowMap& rm, const floa
   g.table = e->W("y_embedder.embedding_table.weight").d; g.labels = y; g.rm = rm;
   g.C2 = e->fp32 ? e->sc_f : nullptr; g.C2h = e->fp32 ? nullptr : e->sc_h;
   launch_gemm_f32(g, s);
+  }
   // every adaLN modulation of the network in one GEMM: mod[rows, NM]
   if (e->fp32) {
     gemm32(e->sc_f, D, e->ada_w, e->ada_b, e->mod, e->NMx, rows, e->NMx, D, F32_EPI_NONE, s);

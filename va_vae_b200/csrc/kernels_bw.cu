@@ -103,6 +103,29 @@ void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowM
 }
 
 // ------------------------------------------------------------------------------------------------
+// c = t_emb + y_emb (lightningdit.py:405) for a batch that shares one timestep (the sampler's case): the timestep
+// MLP ran on a single row; this adds the label row and applies the SiLU that heads every adaLN modulation.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cond_combine(const float* __restrict__ temb, const float* __restrict__ table,
+                               const int64_t* __restrict__ labels, RowMap rm, float* __restrict__ sc_f,
+                               bf16* __restrict__ sc_h, int rows, int D) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * D) return;
+  int r = idx / D, d = idx - r * D;
+  int i;
+  int seg = rm_seg(rm, r, i);
+  float v = temb[d] + table[(size_t)labels[rm.y_off[seg] + i] * D + d];
+  float sv = v / (1.0f + expf(-v));
+  if (sc_f) sc_f[idx] = sv;
+  if (sc_h) sc_h[idx] = __float2bfloat16_rn(sv);
+}
+void launch_cond_combine(const float* temb, const float* table, const int64_t* labels, RowMap rm, float* sc_f, bf16* sc_h,
+                         int rows, int D, cudaStream_t s) {
+  k_cond_combine<<<cdiv(rows * D, 256), 256, 0, s>>>(temb, table, labels, rm, sc_f, sc_h, rows, D);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
 // RMSNorm / LayerNorm + adaLN modulate, one warp per token row, row kept in registers.
 // rmsnorm.py:63,76-77 ; lightningdit.py:26-30.   out = norm(x)*w*(1+scale)+shift
 // ------------------------------------------------------------------------------------------------
