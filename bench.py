@@ -277,7 +277,10 @@ def run_engine(args):
         gpu_launches=int(launches.item()),
         roofline=dict(bound="tensor", kernel="k_gemm_tc<SWIGLU> (mlp.w12, 42.8% of FLOPs)", achieved=roof_achieved,
                       peak=pk["tflops_sustained"], unit="TFLOP/s",
-                      frac=(roof_achieved / pk["tflops_sustained"]) if roof_achieved else None, traffic=None,
+                      frac=(roof_achieved / pk["tflops_sustained"]) if roof_achieved else None,
+                      # dram__bytes_read+write per launch from profiles/r1_w12_ncu.md (B/1, 512-row chunks) vs
+                      # 744.5e6 algorithmic bytes; only valid for that exact launch shape
+                      traffic=(710.9e6 if (args.workload == "b1" and 2 * n >= 512 and not args.chunk) else None),
                       launches_timed=prof_n, peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)"),
     )
     if args.breakdown and rank == 0:

@@ -91,6 +91,7 @@ void launch_patch_embed(const EmbedArgs& a, cudaStream_t s);
 
 void launch_cond_combine(const float* temb, const float* table, const int64_t* labels, RowMap rm, float* sc_f, bf16* sc_h,
                          int rows, int D, cudaStream_t s);
+void launch_patchify_split3(const float* x, bf16* out, int rows, int C, int img, int p, int T, RowMap rm, cudaStream_t s);
 void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowMap rm, cudaStream_t s);
 
 struct NormModArgs {

@@ -64,6 +64,8 @@ struct vavae_engine {
         *U_f = nullptr, *Hh_f = nullptr, *Yfin_f = nullptr;
   // bf16 path
   bf16* A3_h = nullptr;  // [M, 3D] split-bf16 operand of the final linear
+  bf16* Aemb_h = nullptr;   // [M, 3*C*p*p] split-bf16 patches (A operand of the patch-embed GEMM)
+  bf16* embed_w_h = nullptr;  // [D, 3*C*p*p] = [W_hi | W_hi | W_lo]
   bf16 *A_h = nullptr, *q_h = nullptr, *k_h = nullptr, *vt_h = nullptr, *O_h = nullptr, *Hh_h = nullptr;
 
   // sampler state (lazily sized)
@@ -366,6 +368,9 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
         pack_bf16(e, e->W(blk(i, "mlp.fc2.weight")).d, lw.w2, D, S, e->Spad, 0, s);
       }
     }
+    e->embed_w_h = e->alloc<bf16>((size_t)D * 3 * Cpp);
+    k_pack_split3<<<cdiv(D * Cpp, 256), 256, 0, s>>>(e->W("x_embedder.proj.weight").d, e->embed_w_h, D, Cpp);
+    VV_LAUNCH_CHECK();
     e->final_w_h = e->alloc<bf16>((size_t)e->Pout * 3 * D);
     k_pack_split3<<<cdiv(e->Pout * D, 256), 256, 0, s>>>(e->W("final_layer.linear.weight").d, e->final_w_h, e->Pout, D);
     VV_LAUNCH_CHECK();
@@ -411,6 +416,7 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
     e->sc_h = e->alloc<bf16>((size_t)R * D);
     e->A_h = e->alloc<bf16>(M * D);
     e->A3_h = e->alloc<bf16>(M * 3 * D);
+    e->Aemb_h = e->alloc<bf16>(M * 3 * e->C * e->p * e->p);
     if (e->fuse) {
       e->part1 = e->alloc<float>(32 * M, true);
       e->part2 = e->alloc<float>(32 * M, true);
@@ -515,10 +521,19 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
   const int M = rows * T;
   const vavae_config_t& c = e->cfg;
   VV_CHECK(rows <= e->chunk_rows, "forward_chunk: chunk larger than workspace");
-  EmbedArgs ea;
-  ea.x = x; ea.wT = e->embed_wT; ea.bias = e->W("x_embedder.proj.bias").d; ea.pos = e->W("pos_embed").d; ea.X = e->X;
-  ea.rows = rows; ea.C = e->C; ea.img = e->img; ea.p = e->p; ea.D = D; ea.T = T; ea.rm = rm;
-  launch_patch_embed(ea, s);
+  const int Cpp = e->C * e->p * e->p;
+  if (!e->fp32 && (3 * Cpp) % 8 == 0) {
+    // patch embed on the tensor cores: split-bf16 patches x [W_hi | W_hi | W_lo], fp32-grade; epilogue adds bias + pos
+    launch_patchify_split3(x, e->Aemb_h, rows, e->C, e->img, e->p, T, rm, s);
+    TcGemmArgs a = tc_args(e->Aemb_h, 3 * Cpp, e->embed_w_h, 3 * Cpp, M, D, 3 * Cpp, TC_EPI_EMBED, e->W("x_embedder.proj.bias").d);
+    a.out = e->X; a.ldo = D; a.T = T; a.pos = e->W("pos_embed").d;
+    launch_gemm_tc(a, s);
+  } else {
+    EmbedArgs ea;
+    ea.x = x; ea.wT = e->embed_wT; ea.bias = e->W("x_embedder.proj.bias").d; ea.pos = e->W("pos_embed").d; ea.X = e->X;
+    ea.rows = rows; ea.C = e->C; ea.img = e->img; ea.p = e->p; ea.D = D; ea.T = T; ea.rm = rm;
+    launch_patch_embed(ea, s);
+  }
   conditioning(e, rows, rm, t, y, s);
   const float* rcos = c.use_rope ? e->W("feat_rope.freqs_cos").d : nullptr;
   const float* rsin = c.use_rope ? e->W("feat_rope.freqs_sin").d : nullptr;

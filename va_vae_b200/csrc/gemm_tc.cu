@@ -146,7 +146,7 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 
 template <int EPI>
 __device__ __forceinline__ bool epi_fast_supported(const TcGemmArgs& a) {
-  if (EPI == TC_EPI_GATED_RESIDUAL || EPI == TC_EPI_SWIGLU) return true;
+  if (EPI == TC_EPI_GATED_RESIDUAL || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_EMBED) return true;
   if (EPI == TC_EPI_QKV) return a.qn_w == nullptr && a.kn_w == nullptr;
   return false;
 }
@@ -242,6 +242,19 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
           *reinterpret_cast<uint2*>(nxptr + c0 + ps * xpass) =
               make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
         }
+      }
+    } else if (EPI == TC_EPI_EMBED) {
+      // x_embedder(x) + pos_embed (lightningdit.py:402): fp32 residual stream
+      float* xo = reinterpret_cast<float*>(a.out) + (size_t)(wrow0 + prow) * a.ldo + n0 + c0 + pcc;
+      const float* po = a.pos + (size_t)(wt0 + prow) * a.N + n0 + c0 + pcc;
+      float4 p4[LPR];
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) p4[ps] = *reinterpret_cast<const float4*>(po + (size_t)ps * RPP * a.N);
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) {
+        float4 v = lds128(st_r + ps * RPP * SST);
+        v.x += bb.x + p4[ps].x; v.y += bb.y + p4[ps].y; v.z += bb.z + p4[ps].z; v.w += bb.w + p4[ps].w;
+        *reinterpret_cast<float4*>(xo + (size_t)ps * RPP * a.ldo) = v;
       }
     } else if (EPI == TC_EPI_SWIGLU) {
       bf16* ho = reinterpret_cast<bf16*>(a.out) + (size_t)(wrow0 + prow) * a.ldo + ((n0 + c0 + pcc) >> 1);
@@ -804,7 +817,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (row >= a.M || !col_ok) continue;
           float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + pcc);
           v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-          if (EPI == TC_EPI_BIAS_F32) {
+          if (EPI == TC_EPI_EMBED) {
+            const float4 p4 = *reinterpret_cast<const float4*>(a.pos + (size_t)(row % a.T) * a.N + col);
+            v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = v;
+          } else if (EPI == TC_EPI_BIAS_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = v;
           } else if (EPI == TC_EPI_BIAS_BF16 || EPI == TC_EPI_GELU_BF16) {
             if (EPI == TC_EPI_GELU_BF16) {
@@ -983,6 +1000,7 @@ void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
       launch_epi<TC_EPI_QKV>(a, BN, cw, s);
       break;
     case TC_EPI_FINAL: launch_epi<TC_EPI_FINAL>(a, BN, cw, s); break;
+    case TC_EPI_EMBED: launch_epi<TC_EPI_EMBED>(a, BN, cw, s); break;
     default: throw Error("gemm_tc: unknown epilogue");
   }
 }

@@ -12,6 +12,7 @@ enum TcEpi {
   TC_EPI_GELU_BF16 = 4,      // out bf16 = gelu_tanh(acc + bias)                    (legacy mlp.fc1)
   TC_EPI_QKV = 5,            // bias, [qk-norm], RoPE, scatter q,k (B,H,T,hdp) / v^T (B,H,hdv,T)
   TC_EPI_FINAL = 6,          // acc + bias -> unpatchify -> NCHW rows of the caller  (final_layer.linear)
+  TC_EPI_EMBED = 7,          // out f32 [M, ldo] = acc + bias + pos[row % T]          (x_embedder + pos_embed)
 };
 
 struct TcGemmArgs {
@@ -33,6 +34,8 @@ struct TcGemmArgs {
   const float *qn_w, *qn_b, *kn_w, *kn_b;
   int qk_rms;
   int H, hd, hdp, hdv;
+  // embed
+  const float* pos;  // [T, N]
   // final
   int p, Cout, Ckeep, img;
   RowMap rm;

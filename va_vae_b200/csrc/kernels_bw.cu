@@ -81,6 +81,34 @@ void launch_patch_embed(const EmbedArgs& a, cudaStream_t s) {
   VV_LAUNCH_CHECK();
 }
 
+// bf16 path: patchify into the split-bf16 A operand [M, 3*Cpp] = [hi | lo | hi] of the patch-embed GEMM
+// (pairs with the [W_hi | W_hi | W_lo] weight: fp32-grade product on the tensor cores).
+__global__ void k_patchify_split3(const float* __restrict__ x, bf16* __restrict__ out, int rows, int C, int img, int p,
+                                  int T, RowMap rm) {
+  const int pp = p * p, Cpp = C * pp;
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * T * Cpp) return;
+  const int k = (int)(idx % Cpp);
+  const size_t tokg = idx / Cpp;
+  const int tok = (int)(tokg % T), row = (int)(tokg / T);
+  int i;
+  int seg = rm_seg(rm, row, i);
+  const int gw = img / p;
+  const int c = k / pp, ab = k % pp, pa = ab / p, pb = ab % p, ti = tok / gw, tj = tok % gw;
+  const float v = x[(((size_t)(rm.x_off[seg] + i) * C + c) * img + ti * p + pa) * img + tj * p + pb];
+  const bf16 hi = __float2bfloat16_rn(v);
+  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  bf16* o = out + tokg * 3 * Cpp;
+  o[k] = hi;
+  o[Cpp + k] = lo;
+  o[2 * Cpp + k] = hi;
+}
+void launch_patchify_split3(const float* x, bf16* out, int rows, int C, int img, int p, int T, RowMap rm, cudaStream_t s) {
+  size_t total = (size_t)rows * T * C * p * p;
+  k_patchify_split3<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, out, rows, C, img, p, T, rm);
+  VV_LAUNCH_CHECK();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Sinusoidal timestep features [cos | sin], lightningdit.py:121-126 (freqs uploaded from the host so
 // they are bit-identical to the reference's torch.exp).
