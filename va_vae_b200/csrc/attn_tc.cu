@@ -502,12 +502,14 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   const int per_sm = smem <= 113 * 1024 ? 2 : 1;
   const int grid = std::min(n_items, sms * per_sm);
   const bool multi = a.T > AT_BKV;
-  auto go = [&](auto kern) {
-    VV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    kern<<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, tmQt, tmKt, a);
-  };
-  if (multi) go(k_attention_tc<true>);
-  else go(k_attention_tc<false>);
+  static bool attr_set = false;   // not a stream operation: done once, outside any graph capture
+  if (!attr_set) {
+    VV_CUDA(cudaFuncSetAttribute(k_attention_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VV_CUDA(cudaFuncSetAttribute(k_attention_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (multi) k_attention_tc<true><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, tmQt, tmKt, a);
+  else k_attention_tc<false><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, tmQt, tmKt, a);
   VV_LAUNCH_CHECK();
 }
 

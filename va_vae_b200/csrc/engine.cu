@@ -7,6 +7,8 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <set>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -74,6 +76,17 @@ struct vavae_engine {
   int64_t* sy = nullptr;
   float* tgrid_dev = nullptr;
   int tgrid_cap = 0;
+  float* tvec = nullptr;  // [state_rows] per-row t staging for graph-replayed vavae_forward
+
+  // CUDA graphs for the launch-bound small-batch regime: one instantiated graph per (entry point, batch, input buffer)
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    size_t nodes = 0;
+  };
+  std::map<std::string, GraphEntry> graphs;
+  std::set<std::string> graph_warm;
+  cudaStream_t gstream = nullptr;
+  int graph_max_rows = 128;  // model rows up to which evaluations are replayed from a graph (VAVAE_GRAPH_MAX_ROWS)
 
   template <typename Tp>
   Tp* alloc(size_t n, bool zero = false) {
@@ -712,7 +725,53 @@ static void ensure_state(vavae_engine* e, int rows) {
   }
   if (e->sy) e->release(e->sy);
   e->sy = e->alloc<int64_t>(rows);
+  if (e->tvec) e->release(e->tvec);
+  e->tvec = e->alloc<float>(rows);
+  // buffers moved: graphs that baked the old addresses are stale
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);
+  e->graphs.clear();
+  e->graph_warm.clear();
   e->state_rows = rows;
+}
+
+// Runs `launch(stream)` -- a fixed kernel sequence on engine-owned buffers -- through a CUDA graph: the first call
+// with a given key runs eagerly (sets function attributes, warms caches), the second captures it on the engine's
+// private stream (the caller's may be the legacy default stream, which cannot be captured) and every call from
+// then on is a single cudaGraphLaunch on the caller's stream.
+static void run_graphed(vavae_engine* e, const std::string& key, const std::function<void(cudaStream_t)>& launch,
+                        cudaStream_t s) {
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    if (!e->graph_warm.count(key)) {
+      e->graph_warm.insert(key);
+      launch(s);
+      return;
+    }
+    if (e->graphs.size() >= 16) {
+      for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);
+      e->graphs.clear();
+    }
+    if (!e->gstream) VV_CUDA(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    const uint64_t before = e->counter.n;
+    VV_CUDA(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
+    try {
+      launch(e->gstream);
+    } catch (...) {
+      cudaStreamEndCapture(e->gstream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    VV_CUDA(cudaStreamEndCapture(e->gstream, &graph));
+    vavae_engine::GraphEntry ge;
+    ge.nodes = (size_t)(e->counter.n - before);
+    e->counter.n = before;  // captured launches did not execute; replays are counted below
+    VV_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
+    VV_CUDA(cudaGraphDestroy(graph));
+    it = e->graphs.emplace(key, ge).first;
+  }
+  VV_CUDA(cudaGraphLaunch(it->second.exec, s));
+  e->counter.n += it->second.nodes;
 }
 
 static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const float* t_grid, int n_points, int method,
@@ -731,13 +790,32 @@ static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const 
   const size_t per = (size_t)e->C * e->img * e->img;
   const size_t state_bytes = (size_t)batch * per * sizeof(float);
   VV_CUDA(cudaMemcpyAsync(e->tgrid_dev, t_grid, (size_t)n_points * sizeof(float), cudaMemcpyHostToDevice, s));
-  float* xs = out_final;  // integrate in place in the caller's output buffer
+  // Small batches are launch-bound (an XL forward is ~230 launches): integrate on engine-owned buffers so one
+  // evaluation is a fixed kernel sequence and replay it from a CUDA graph.
+  const bool graphed = batch <= e->graph_max_rows && e->prof_kernel < 0;
+  float* xs = out_final;  // large batches: integrate in place in the caller's output buffer
+  const int64_t* yy = y;
+  if (graphed) {
+    xs = e->sx;
+    if (y != e->sy) VV_CUDA(cudaMemcpyAsync(e->sy, y, (size_t)batch * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    yy = e->sy;
+  }
   if (xs != z) VV_CUDA(cudaMemcpyAsync(xs, z, state_bytes, cudaMemcpyDeviceToDevice, s));
   int eval = 0;
   auto eval_model = [&](const float* xin, int tidx) {
+    if (graphed) {
+      // the evaluation time goes through a fixed device scalar so the captured kernels never change
+      VV_CUDA(cudaMemcpyAsync(e->st, e->tgrid_dev + tidx, sizeof(float), cudaMemcpyDeviceToDevice, s));
+      const std::string key = std::string("S") + (use_cfg ? "c" : "p") + (xin == e->sxp ? "1" : "0") + "_" + std::to_string(batch);
+      run_graphed(e, key, [&](cudaStream_t gs) {
+        if (use_cfg) forward_pairs(e, xin, e->st, 0, yy, e->sv, batch / 2, gs);
+        else forward_plain(e, xin, e->st, 0, yy, e->sv, batch, gs);
+      }, s);
+      return;
+    }
     const float* tp = e->tgrid_dev + tidx;  // every row uses the same time: t_stride = 0
-    if (use_cfg) forward_pairs(e, xin, tp, 0, y, e->sv, batch / 2, s);
-    else forward_plain(e, xin, tp, 0, y, e->sv, batch, s);
+    if (use_cfg) forward_pairs(e, xin, tp, 0, yy, e->sv, batch / 2, s);
+    else forward_plain(e, xin, tp, 0, yy, e->sv, batch, s);
   };
   OdeArgs o;
   o.v = e->sv; o.x = xs; o.xp = e->sxp; o.k1 = e->sk1; o.rows = batch; o.C = e->C; o.HW = e->img * e->img;
@@ -764,6 +842,7 @@ static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const 
       launch_ode_update(o, s);
     }
   }
+  if (xs != out_final) VV_CUDA(cudaMemcpyAsync(out_final, xs, state_bytes, cudaMemcpyDeviceToDevice, s));
 }
 
 // --------------------------------------------------------------------------------------------- C ABI
@@ -802,6 +881,7 @@ int vavae_create(const vavae_config_t* cfg, int device, vavae_engine_t** out) {
     e->cfg = *cfg;
     e->device = device;
     derive(e);
+    if (const char* gm = std::getenv("VAVAE_GRAPH_MAX_ROWS")) e->graph_max_rows = std::atoi(gm);
     *out = e;
     return 0;
   } catch (const std::exception& ex) {
@@ -815,6 +895,9 @@ int vavae_destroy(vavae_engine_t* e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);
+  if (e->gstream) cudaStreamDestroy(e->gstream);
+  for (cudaEvent_t ev : e->prof_ev) cudaEventDestroy(ev);
   for (void* p : e->owned)
     if (p) cudaFree(p);
   delete e;
@@ -856,7 +939,20 @@ int vavae_forward(vavae_engine_t* e, const float* x, const float* t, const int64
   VV_API_BEGIN(e)
   VV_CHECK(e && e->finalized, "engine not finalized");
   VV_CHECK(batch > 0, "empty batch");
-  forward_plain(e, x, t, 1, y, out, batch, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (batch <= e->graph_max_rows && e->prof_kernel < 0) {
+    // launch-bound regime: stage the inputs in engine-owned buffers and replay the forward from a CUDA graph
+    ensure_state(e, batch);
+    const size_t per = (size_t)e->C * e->img * e->img;
+    VV_CUDA(cudaMemcpyAsync(e->sx, x, (size_t)batch * per * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    VV_CUDA(cudaMemcpyAsync(e->tvec, t, (size_t)batch * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    VV_CUDA(cudaMemcpyAsync(e->sy, y, (size_t)batch * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    run_graphed(e, "F_" + std::to_string(batch),
+                [&](cudaStream_t gs) { forward_plain(e, e->sx, e->tvec, 1, e->sy, e->sv, batch, gs); }, s);
+    VV_CUDA(cudaMemcpyAsync(out, e->sv, (size_t)batch * per * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    forward_plain(e, x, t, 1, y, out, batch, s);
+  }
   VV_API_END()
 }
 
