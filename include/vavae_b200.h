@@ -103,6 +103,16 @@ int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t*
                           int n_points, int method, int use_cfg, float cfg_scale, int cfg_interval,
                           float cfg_interval_start, int cfg_channels, float* out_final_host, int batch, void* stream);
 
+/* Replaces sample_fn built with sampling_method="dopri5" (the default of Sampler.sample_ode, transport/transport.py:401,
+ * and what the fork's generation scripts use): adaptive Dormand-Prince 5(4) from t0 to t1 with torchdiffeq's step
+ * controller (RMS error norm over the whole state, atol/rtol, safety 0.9, ifactor 10, dfactor 0.2, Hairer initial
+ * step, FSAL, dense output at t1).  torchdiffeq is not vendored by the reference: parity for this entry point is
+ * pinned only against this repo's restatement of that algorithm.  Synchronises the stream once per step
+ * (the controller needs the error norm on the host).  stats (optional, host): {accepted, rejected, evaluations}. */
+int vavae_sample_dopri5(vavae_engine_t* e, const float* z, const int64_t* y, double t0, double t1, double atol, double rtol,
+                        int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start, int cfg_channels,
+                        float* out_final, int batch, int64_t* stats, void* stream);
+
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 uint64_t vavae_launch_count(const vavae_engine_t* e);
 /* Bytes of device memory the engine owns (weights + workspace). */

@@ -326,7 +326,7 @@ def time_grid(num_steps: int, timestep_shift: float = 0.0, t0: float = 0.0, t1: 
 
 @torch.no_grad()
 def sample_ode(cfg, sd, z, y, grid, method="euler", cfg_scale=None, cfg_interval=None,
-               cfg_interval_start=None, return_trace=False):
+               cfg_interval_start=None, return_trace=False, atol=1e-6, rtol=1e-3):
     """ode.sample (transport/integrators.py:107-126) with the fixed-grid torchdiffeq semantics:
     one step per grid interval; euler y1 = y0 + dt*f(t0,y0); heun (explicit trapezoid)
     y1 = y0 + dt/2*(k1 + f(t1, y0 + dt*k1)).  The drift is the identity velocity wrapper
@@ -338,6 +338,9 @@ def sample_ode(cfg, sd, z, y, grid, method="euler", cfg_scale=None, cfg_interval
             return forward(cfg, sd, x, tv, y)
         return forward_with_cfg(cfg, sd, x, tv, y, cfg_scale, cfg_interval, cfg_interval_start)
 
+    if method == "dopri5":
+        from oracle.dopri5 import odeint_dopri5
+        return odeint_dopri5(lambda t, x: f(t, x), z, grid, atol=atol, rtol=rtol)[-1]
     x, trace = z, []
     for j in range(len(grid) - 1):
         t0, t1 = grid[j], grid[j + 1]

@@ -63,8 +63,13 @@ class _Mlp(nn.Module):
 
 def fixed_grid_odeint(func, y0, t, method="euler", atol=None, rtol=None, **_):
     """Fixed-grid euler / heun over the grid ``t``; returns stack([y_0, ..., y_{P-1}])."""
+    if method == "dopri5":
+        from oracle.dopri5 import odeint_dopri5      # restated adaptive solver (parity unpinned, see its header)
+        a = atol[0] if isinstance(atol, (list, tuple)) else atol
+        r = rtol[0] if isinstance(rtol, (list, tuple)) else rtol
+        return odeint_dopri5(func, y0, t, atol=a, rtol=r)
     if method not in ("euler", "heun", "heun2"):
-        raise ValueError(f"shim supports fixed-grid euler/heun only, got {method!r}")
+        raise ValueError(f"shim supports euler/heun/dopri5 only, got {method!r}")
     ys = [y0]
     y = y0
     for j in range(len(t) - 1):

@@ -169,6 +169,32 @@ struct OdeArgs {
 };
 void launch_ode_update(const OdeArgs& a, cudaStream_t s);
 
+// ---- adaptive RK (dopri5) helpers
+struct RkCombineArgs {
+  const float* y0;
+  const float* k[7];
+  float coef[7];   // already multiplied by dt
+  int nk;
+  float* out;
+  size_t n4;       // number of float4 elements
+};
+void launch_rk_combine(const RkCombineArgs& a, cudaStream_t s);
+struct RkNormArgs {
+  const float* k[7];
+  float coef[7];
+  int nk;
+  const float* sub;   // optional: subtracted from the combination
+  const float* y0;
+  const float* y1;    // optional
+  float atol, rtol;
+  double* partial;    // [blocks]
+  int blocks;
+  size_t n;
+};
+void launch_rk_sqnorm(const RkNormArgs& a, double* out, cudaStream_t s);
+void launch_rk_interp(const float* y0, const float* y1, const float* ymid, const float* f0, const float* f1, float dt,
+                      float x, float* out, size_t n, cudaStream_t s);
+
 void launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
 
 }  // namespace vv

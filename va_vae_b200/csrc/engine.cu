@@ -9,6 +9,8 @@
 #include <map>
 #include <set>
 #include <cstdlib>
+#include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -76,6 +78,11 @@ struct vavae_engine {
   int64_t* sy = nullptr;
   float* tgrid_dev = nullptr;
   int tgrid_cap = 0;
+  // adaptive RK (dopri5) state: y0, y1, ymid, ytmp + 7 stage derivatives, sized like the sampler state
+  int rk_rows = 0;
+  float* rk[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* rk_partial = nullptr;
+  double* rk_sum = nullptr;
   float* tvec = nullptr;  // [state_rows] per-row t staging for graph-replayed vavae_forward
 
   // CUDA graphs for the launch-bound small-batch regime: one instantiated graph per (entry point, batch, input buffer)
@@ -845,6 +852,147 @@ static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const 
   if (xs != out_final) VV_CUDA(cudaMemcpyAsync(out_final, xs, state_bytes, cudaMemcpyDeviceToDevice, s));
 }
 
+// --------------------------------------------------------------------------------------------- adaptive dopri5
+// Dormand-Prince 5(4) with the step controller the reference reaches through torchdiffeq.odeint(method="dopri5")
+// (transport/integrators.py:118-125; the package is not vendored - semantics restated from its published algorithm:
+// Hairer initial step, RMS error norm over the whole state, safety 0.9, ifactor 10, dfactor 0.2, order 5, FSAL,
+// 4th-order dense output).  Step-size control runs on the host in double precision with one 8-byte D2H read per
+// step (torchdiffeq synchronises per step as well); every tensor operation is a kernel of this library.
+static const double kDpAlpha[6] = {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+static const double kDpBeta[6][6] = {
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+static const double kDpErr[7] = {35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+                                 -2187.0 / 6784 - -12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60};
+static const double kDpMid[7] = {6025192743.0 / 30085553152.0 / 2, 0, 51252292925.0 / 65400821598.0 / 2,
+                                 -2691868925.0 / 45128329728.0 / 2, 187940372067.0 / 1594534317056.0 / 2,
+                                 -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
+
+static void sample_dopri5(vavae_engine* e, const float* z, const int64_t* y, double t0, double t1, double atol,
+                          double rtol, int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start,
+                          int cfg_channels, float* out_final, int batch, int64_t* stats, cudaStream_t s) {
+  VV_CHECK(t0 < t1, "ODE sampler has to be in forward time");
+  VV_CHECK(!use_cfg || batch % 2 == 0, "sample_dopri5: CFG batch must be even");
+  ensure_state(e, batch);
+  const size_t per = (size_t)e->C * e->img * e->img;
+  const size_t n = (size_t)batch * per;
+  if (batch > e->rk_rows) {
+    for (int i = 0; i < 11; ++i) {
+      if (e->rk[i]) e->release(e->rk[i]);
+      e->rk[i] = e->alloc<float>(n);
+    }
+    if (!e->rk_partial) {
+      e->rk_partial = e->alloc<double>(1024);
+      e->rk_sum = e->alloc<double>(1);
+    }
+    e->rk_rows = batch;
+  }
+  float *y0 = e->rk[0], *y1 = e->rk[1], *ymid = e->rk[2], *ytmp = e->rk[3];
+  float* k[7];
+  for (int i = 0; i < 7; ++i) k[i] = e->rk[4 + i];
+  VV_CUDA(cudaMemcpyAsync(y0, z, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  int64_t n_evals = 0, n_accept = 0, n_reject = 0;
+
+  // f(t, yin) -> kout : the drift the reference integrates (forward_with_cfg / forward), evaluated at float32 t
+  auto f = [&](float tval, const float* yin, float* kout) {
+    VV_CUDA(cudaMemcpyAsync(e->st, &tval, sizeof(float), cudaMemcpyHostToDevice, s));
+    if (use_cfg) {
+      forward_pairs(e, yin, e->st, 0, y, e->sv, batch / 2, s);
+      CfgArgs c;
+      c.v = e->sv; c.out = kout; c.t = e->st; c.n = batch / 2; c.C = e->C; c.HW = e->img * e->img; c.scale = cfg_scale;
+      c.interval = cfg_interval; c.start = cfg_interval_start; c.channels = cfg_channels;
+      launch_cfg_combine(c, s);
+    } else {
+      forward_plain(e, yin, e->st, 0, y, kout, batch, s);
+    }
+    ++n_evals;
+  };
+  auto norm = [&](const float* const* kk, const double* coef, int nk, const float* sub, const float* ya, const float* yb) {
+    RkNormArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int j = 0; j < nk; ++j) { a.k[j] = kk[j]; a.coef[j] = (float)coef[j]; }
+    a.nk = nk; a.sub = sub; a.y0 = ya; a.y1 = yb; a.atol = (float)atol; a.rtol = (float)rtol;
+    a.partial = e->rk_partial; a.blocks = (int)std::min<size_t>(1024, (n + 255) / 256); a.n = n;
+    launch_rk_sqnorm(a, e->rk_sum, s);
+    double sum = 0.0;
+    VV_CUDA(cudaMemcpyAsync(&sum, e->rk_sum, sizeof(double), cudaMemcpyDeviceToHost, s));
+    VV_CUDA(cudaStreamSynchronize(s));
+    return std::sqrt(sum / (double)n);   // RMS norm over the whole state
+  };
+  auto combine = [&](const float* base, const double* coef, int nk, double dt, float* out) {
+    RkCombineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.y0 = base; a.nk = nk; a.out = out; a.n4 = n / 4;
+    for (int j = 0; j < nk; ++j) { a.k[j] = k[j]; a.coef[j] = (float)((float)coef[j] * (float)dt); }
+    launch_rk_combine(a, s);
+  };
+
+  // ---- initial step (Hairer, Norsett & Wanner II.4, as used by torchdiffeq), order = 4
+  f((float)t0, y0, k[0]);
+  const double one = 1.0;
+  const float* y0p[1] = {y0};
+  const float* f0p[1] = {k[0]};
+  const double d0 = norm(y0p, &one, 1, nullptr, y0, nullptr);
+  const double d1 = norm(f0p, &one, 1, nullptr, y0, nullptr);
+  double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+  {
+    const double c1 = 1.0;
+    combine(y0, &c1, 1, h0, ytmp);                       // y0 + h0 * f0
+    f((float)(t0 + h0), ytmp, k[1]);
+  }
+  const float* f1p[1] = {k[1]};
+  const double d2 = norm(f1p, &one, 1, k[0], y0, nullptr) / h0;
+  double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? std::max(1e-6, h0 * 1e-3) : std::pow(0.01 / std::max(d1, d2), 1.0 / 5.0);
+  double dt = std::min(100.0 * h0, h1);
+
+  // ---- adaptive steps until the accepted interval covers t1, then dense output at t1
+  double t = t0;
+  const int max_steps = 100000;
+  for (int it = 0;; ++it) {
+    VV_CHECK(it < max_steps, "dopri5: max_num_steps exceeded");
+    const float dtf = (float)dt, tf = (float)t;
+    for (int i = 0; i < 6; ++i) {
+      float* yi = (i == 5) ? y1 : ytmp;                  // the last stage input is the 5th-order solution (FSAL)
+      combine(y0, kDpBeta[i], i + 1, dt, yi);
+      const float ti = (kDpAlpha[i] == 1.0) ? (float)(t + dt) : tf + (float)kDpAlpha[i] * dtf;
+      f(ti, yi, k[i + 1]);
+    }
+    double cerr[7];
+    for (int j = 0; j < 7; ++j) cerr[j] = (double)((float)kDpErr[j] * dtf);
+    const float* kc[7] = {k[0], k[1], k[2], k[3], k[4], k[5], k[6]};
+    const double ratio = norm(kc, cerr, 7, nullptr, y0, y1);
+    const bool accept = ratio <= 1.0;
+    if (accept) {
+      ++n_accept;
+      if (t + dt >= t1) {
+        combine(y0, kDpMid, 7, dt, ymid);
+        const float x = (float)((t1 - t) / dt);
+        launch_rk_interp(y0, y1, ymid, k[0], k[6], dtf, x, out_final, n, s);
+        break;
+      }
+      std::swap(y0, y1);
+      std::swap(k[0], k[6]);
+      t += dt;
+    } else {
+      ++n_reject;
+    }
+    // torchdiffeq _optimal_step_size(dt, ratio, safety=0.9, ifactor=10, dfactor=0.2, order=5)
+    double factor;
+    if (ratio == 0.0) factor = 10.0;
+    else factor = std::min(10.0, std::max(0.9 / std::pow(ratio, 1.0 / 5.0), ratio < 1.0 ? 1.0 : 0.2));
+    dt *= factor;
+  }
+  if (stats) {
+    stats[0] = n_accept;
+    stats[1] = n_reject;
+    stats[2] = n_evals;
+  }
+}
+
 // --------------------------------------------------------------------------------------------- C ABI
 #define VV_API_BEGIN(e)                 \
   try {                                 \
@@ -998,6 +1146,18 @@ int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t*
              cfg_channels, e->sx, nullptr, batch, s);
   VV_CUDA(cudaMemcpyAsync(out_final_host, e->sx, bytes, cudaMemcpyDeviceToHost, s));
   VV_CUDA(cudaStreamSynchronize(s));
+  VV_API_END()
+}
+
+int vavae_sample_dopri5(vavae_engine_t* e, const float* z, const int64_t* y, double t0, double t1, double atol, double rtol,
+                        int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start, int cfg_channels,
+                        float* out_final, int batch, int64_t* stats, void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && e->finalized, "engine not finalized");
+  VV_CHECK(batch > 0 && z && y && out_final, "null / empty argument");
+  VV_CHECK(atol > 0 && rtol > 0, "dopri5 tolerances must be positive");
+  sample_dopri5(e, z, y, t0, t1, atol, rtol, use_cfg, cfg_scale, cfg_interval, cfg_interval_start, cfg_channels, out_final,
+                batch, stats, (cudaStream_t)stream);
   VV_API_END()
 }
 

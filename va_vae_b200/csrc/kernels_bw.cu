@@ -554,3 +554,96 @@ void launch_f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {
 }
 
 }  // namespace vv
+
+// ================================================================================================
+// Adaptive Dormand-Prince 5(4) support kernels (vavae_sample_dopri5): stage combination, scaled error / step-size
+// norms (deterministic two-stage reduction), dense-output evaluation.
+// ================================================================================================
+namespace vv {
+
+__global__ void k_rk_combine(RkCombineArgs a) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n4) return;
+  float4 acc = reinterpret_cast<const float4*>(a.y0)[i];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    if (j < a.nk && a.coef[j] != 0.f) {
+      const float4 k = reinterpret_cast<const float4*>(a.k[j])[i];
+      const float c = a.coef[j];
+      acc.x += c * k.x; acc.y += c * k.y; acc.z += c * k.z; acc.w += c * k.w;
+    }
+  }
+  reinterpret_cast<float4*>(a.out)[i] = acc;
+}
+void launch_rk_combine(const RkCombineArgs& a, cudaStream_t s) {
+  k_rk_combine<<<(unsigned)((a.n4 + 255) / 256), 256, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+// partial[block] = sum over the block's elements of ((sum_j coef_j k_j - sub) / (atol + rtol * max(|y0|, |y1|)))^2
+// (y1 may be null -> |y0| only; sub may be null).  Fixed grid + fixed in-block order => deterministic.
+__global__ void __launch_bounds__(256) k_rk_sqnorm(RkNormArgs a) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j < a.nk && a.coef[j] != 0.f) v += a.coef[j] * a.k[j][i];
+    if (a.sub) v -= a.sub[i];
+    float m = fabsf(a.y0[i]);
+    if (a.y1) m = fmaxf(m, fabsf(a.y1[i]));
+    const float r = v / (a.atol + a.rtol * m);
+    acc += (double)r * (double)r;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    a.partial[blockIdx.x] = t;
+  }
+}
+__global__ void k_rk_reduce(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += partial[i];
+    out[0] = t;
+  }
+}
+void launch_rk_sqnorm(const RkNormArgs& a, double* out, cudaStream_t s) {
+  k_rk_sqnorm<<<a.blocks, 256, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+  k_rk_reduce<<<1, 32, 0, s>>>(a.partial, a.blocks, out);
+  VV_LAUNCH_CHECK();
+}
+
+// dense output of one accepted step (4th-order polynomial through y0, y_mid, y1 with end slopes f0, f1) at x in [0,1]
+__global__ void k_rk_interp(const float* __restrict__ y0, const float* __restrict__ y1, const float* __restrict__ ymid,
+                            const float* __restrict__ f0, const float* __restrict__ f1, float dt, float x,
+                            float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a0 = y0[i], a1 = y1[i], am = ymid[i], g0 = f0[i], g1 = f1[i];
+  const float ca = 2.f * dt * (g1 - g0) - 8.f * (a1 + a0) + 16.f * am;
+  const float cb = dt * (5.f * g0 - 3.f * g1) + 18.f * a0 + 14.f * a1 - 32.f * am;
+  const float cc = dt * (g1 - 4.f * g0) - 11.f * a0 - 5.f * a1 + 16.f * am;
+  const float cd = dt * g0;
+  float total = a0 + x * cd;
+  float xp = x * x;
+  total += xp * cc;
+  xp *= x;
+  total += xp * cb;
+  xp *= x;
+  total += xp * ca;
+  out[i] = total;
+}
+void launch_rk_interp(const float* y0, const float* y1, const float* ymid, const float* f0, const float* f1, float dt,
+                      float x, float* out, size_t n, cudaStream_t s) {
+  k_rk_interp<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y0, y1, ymid, f0, f1, dt, x, out, n);
+  VV_LAUNCH_CHECK();
+}
+
+}  // namespace vv

@@ -23,7 +23,7 @@ EXPORTS = [
     "vavae_abi_version", "vavae_last_error", "vavae_create", "vavae_destroy", "vavae_load_weight", "vavae_finalize",
     "vavae_forward", "vavae_forward_with_cfg", "vavae_sample_ode", "vavae_sample_ode_host", "vavae_launch_count",
     "vavae_device_bytes", "vavae_test_gemm_bf16", "vavae_test_attention_bf16", "vavae_time_kernel",
-    "vavae_profile_begin", "vavae_profile_end", "vavae_set_gemm_two_cta",
+    "vavae_profile_begin", "vavae_profile_end", "vavae_set_gemm_two_cta", "vavae_sample_dopri5",
 ]
 
 
@@ -61,6 +61,9 @@ def load_library() -> ctypes.CDLL:
                                      c_int, c_float, c_int, c_void, c_void, c_int, c_void]
     lib.vavae_sample_ode_host.argtypes = [c_void, c_void, c_void, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float,
                                           c_int, c_float, c_int, c_void, c_int, c_void]
+    lib.vavae_sample_dopri5.argtypes = [c_void, c_void, c_void, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_double, c_int, c_float, c_int, c_float, c_int, c_void, c_int,
+                                        ctypes.POINTER(ctypes.c_int64), c_void]
     lib.vavae_launch_count.argtypes = [c_void]
     lib.vavae_launch_count.restype = ctypes.c_uint64
     lib.vavae_device_bytes.argtypes = [c_void]
@@ -194,6 +197,25 @@ class Engine:
                 interval, start, int(cfg_channels), out.data_ptr(), trace.data_ptr() if return_trace else None,
                 z.shape[0], ctypes.c_void_p(_stream(self.device))))
         return (out, trace) if return_trace else out
+
+    # -- adaptive dopri5 (torchdiffeq.odeint(method="dopri5") as reached from transport/integrators.py:118-125)
+    def sample_dopri5(self, z, y, t0=0.0, t1=1.0, atol=1e-6, rtol=1e-3, use_cfg=True, cfg_scale=1.0, cfg_interval=None,
+                      cfg_interval_start=None, cfg_channels=3, return_stats=False):
+        z = _f32(z, self.device)
+        y = y.to(device=self.device, dtype=torch.int64).contiguous()
+        self._check_x(z)
+        out = torch.empty_like(z)
+        interval = 1 if cfg_interval is True else 0
+        start = float(cfg_interval_start) if (interval and cfg_interval_start is not None) else 0.0
+        stats = (ctypes.c_int64 * 3)()
+        with torch.cuda.device(self.device):
+            _check(self._lib.vavae_sample_dopri5(
+                self._h, z.data_ptr(), y.data_ptr(), float(t0), float(t1), float(atol), float(rtol), 1 if use_cfg else 0,
+                float(cfg_scale), interval, start, int(cfg_channels), out.data_ptr(), z.shape[0], stats,
+                ctypes.c_void_p(_stream(self.device))))
+        if return_stats:
+            return out, dict(accepted=stats[0], rejected=stats[1], evals=stats[2])
+        return out
 
     def sample_ode_host(self, z_host, y_host, t_grid, out_host, method="euler", use_cfg=True, cfg_scale=1.0,
                         cfg_interval=None, cfg_interval_start=None, cfg_channels=3):

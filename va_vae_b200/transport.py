@@ -155,11 +155,21 @@ class ode:
 
     def sample(self, x, model, **model_kwargs):
         method = self.sampler_type
-        if method not in ("euler", "heun", "heun2"):
+        if method not in ("euler", "heun", "heun2", "dopri5"):
             raise NotImplementedError(f"sampling_method={method!r}: the B200 engine implements the fixed-grid "
-                                      "solvers 'euler' and 'heun'; adaptive dopri5 is a planned follow-up "
-                                      "(SURVEY.md section 8f)")
+                                      "solvers 'euler' / 'heun' and the adaptive 'dopri5'")
         owner, name = self._native_target(model)
+        if owner is not None and method == "dopri5":
+            eng = owner.engine()
+            owner._require_eval()
+            cfg = name == "forward_with_cfg"
+            final = eng.sample_dopri5(x, model_kwargs["y"], float(self.t[0]), float(self.t[-1]), self.atol, self.rtol,
+                                      cfg, model_kwargs.get("cfg_scale", 1.0), model_kwargs.get("cfg_interval"),
+                                      model_kwargs.get("cfg_interval_start"), 3)
+            return LazyTrajectory(final, len(self.t))
+        if method == "dopri5":
+            return _dopri5_generic(lambda tt, yy: self.drift(yy, th.ones(yy.size(0)).to(yy.device) * tt, model, **model_kwargs),
+                                   x, self.t.to(x.device), self.atol, self.rtol)
         if owner is not None:
             eng = owner.engine()
             owner._require_eval()
@@ -184,6 +194,70 @@ class ode:
                 y = y + (dt * 0.5) * (k1 + k2)
             ys.append(y)
         return th.stack(ys)
+
+
+_DP_ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+_DP_BETA = [[1 / 5], [3 / 40, 9 / 40], [44 / 45, -56 / 15, 32 / 9],
+            [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+            [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+            [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]]
+_DP_ERR = [35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+           -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1. / 60.]
+_DP_MID = [6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+           187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2]
+
+
+@th.no_grad()
+def _dopri5_generic(func, y0, t, atol, rtol, max_num_steps=100000):
+    """Adaptive Dormand-Prince 5(4) for an arbitrary drift callable (host loop over torch tensors): the algorithm
+    torchdiffeq.odeint(method="dopri5") applies -- Hairer initial step, RMS error norm, safety 0.9 / ifactor 10 /
+    dfactor 0.2, FSAL, outputs by 4th-order dense interpolation.  Returns stack of the solution at every t."""
+    dtype = y0.dtype
+    rms = lambda v: float(v.double().pow(2).mean().sqrt())
+    sc = lambda v: th.tensor(v, dtype=dtype, device=y0.device)
+    times = [float(v) for v in t]
+    f = lambda tt, yy: func(sc(tt), yy)
+    t0 = times[0]
+    f0 = f(t0, y0)
+    scale = atol + y0.abs() * rtol
+    d0, d1 = rms(y0 / scale), rms(f0 / scale)
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = f(t0 + h0, y0 + sc(h0) * f0)
+    d2 = rms((f1 - f0) / scale) / h0
+    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** 0.2
+    dt = min(100 * h0, h1)
+    out, tcur, ycur, fcur, seg = [y0], t0, y0, f0, None
+    for next_t in times[1:]:
+        steps = 0
+        while seg is None or next_t > seg[1]:
+            steps += 1
+            if steps > max_num_steps:
+                raise RuntimeError("max_num_steps exceeded")
+            dtf, ks, yi = sc(dt), [fcur], None
+            for i in range(6):
+                yi = ycur
+                for j in range(i + 1):
+                    if _DP_BETA[i][j] != 0:
+                        yi = yi + (sc(_DP_BETA[i][j]) * dtf) * ks[j]
+                ti = float(sc(tcur + dt)) if _DP_ALPHA[i] == 1.0 else float(sc(tcur) + sc(_DP_ALPHA[i]) * dtf)
+                ks.append(f(ti, yi))
+            err = sum((sc(_DP_ERR[j]) * dtf) * ks[j] for j in range(7) if _DP_ERR[j] != 0)
+            ratio = rms(err / (atol + rtol * th.max(ycur.abs(), yi.abs())))
+            if ratio <= 1:
+                ymid = ycur
+                for j in range(7):
+                    if _DP_MID[j] != 0:
+                        ymid = ymid + (sc(_DP_MID[j]) * dtf) * ks[j]
+                seg = (tcur, tcur + dt, ycur, yi, ymid, fcur, ks[-1], dtf)
+                tcur, ycur, fcur = tcur + dt, yi, ks[-1]
+            dt = dt * (10.0 if ratio == 0 else min(10.0, max(0.9 / ratio ** 0.2, 1.0 if ratio < 1 else 0.2)))
+        ts, te, a0, a1, am, g0, g1, dtf = seg
+        x = sc((next_t - ts) / (te - ts))
+        ca = 2 * dtf * (g1 - g0) - 8 * (a1 + a0) + 16 * am
+        cb = dtf * (5 * g0 - 3 * g1) + 18 * a0 + 14 * a1 - 32 * am
+        cc = dtf * (g1 - 4 * g0) - 11 * a0 - 5 * a1 + 16 * am
+        out.append(a0 + x * (dtf * g0) + x * x * cc + x * x * x * cb + x * x * x * x * ca)
+    return th.stack(out)
 
 
 class Sampler:
