@@ -56,6 +56,7 @@ struct vavae_engine {
   float* ada_w = nullptr;     // fp32 mode: [NM, D]
   float* ada_b = nullptr;     // [NM]
   // packed (bf16 mode)
+  float* rope_cs = nullptr;   // [T, hd/2, 2] interleaved (cos, sin) when the tables repeat each frequency twice
   bf16* ada_w_h = nullptr;    // [NM, D]
   bf16* final_w_h = nullptr;  // [Pout, D]
   std::vector<LayerBf16> lw;
@@ -362,6 +363,21 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
     VV_CUDA(cudaStreamSynchronize(s));
     e->release(waT); e->release(wc); e->release(bc);
   }
+  if (!e->fp32 && c.use_rope && hd % 2 == 0) {
+    // RoPE tables of the reference repeat every frequency twice (pos_embed.py:123-128): if this state_dict's do too,
+    // keep one (cos, sin) pair per rotation pair -> half the table traffic in the QKV epilogue
+    std::vector<float> hc((size_t)T * hd), hs((size_t)T * hd);
+    VV_CUDA(cudaMemcpy(hc.data(), e->W("feat_rope.freqs_cos").d, hc.size() * 4, cudaMemcpyDeviceToHost));
+    VV_CUDA(cudaMemcpy(hs.data(), e->W("feat_rope.freqs_sin").d, hs.size() * 4, cudaMemcpyDeviceToHost));
+    bool paired = true;
+    for (size_t i = 0; i < hc.size() && paired; i += 2) paired = hc[i] == hc[i + 1] && hs[i] == hs[i + 1];
+    if (paired) {
+      std::vector<float> cs((size_t)T * hd);
+      for (size_t i = 0; i < hc.size(); i += 2) { cs[i] = hc[i]; cs[i + 1] = hs[i]; }
+      e->rope_cs = e->alloc<float>(cs.size());
+      VV_CUDA(cudaMemcpy(e->rope_cs, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
   if (!e->fp32) {
     e->lw.resize(L);
     for (int i = 0; i < L; ++i) {
@@ -599,7 +615,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
     } else {
       const float* bqkv = e->W(blk(i, "attn.qkv.bias")).d;
       TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].qkv, D, M, 3 * D, D, TC_EPI_QKV, bqkv);
-      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
+      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
       a.kn_b = knb; a.qk_rms = c.use_rmsnorm; a.H = H; a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
       if (fuse && i > 0) {
         a.in_part = e->part2; a.in_nparts = np_w3; a.in_dim = D;
@@ -1247,7 +1263,7 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     *work = 2.0 * M * 3.0 * D * D;
     fn = [&] {
       TcGemmArgs a = tc_args(e->A_h, D, e->lw[0].qkv, D, M, 3 * D, D, TC_EPI_QKV, e->W(blk(0, "attn.qkv.bias")).d);
-      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.qk_rms = c.use_rmsnorm; a.H = H;
+      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.qk_rms = c.use_rmsnorm; a.H = H;
       a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
       if (c.use_qknorm) { a.qn_w = e->W(blk(0, "attn.q_norm.weight")).d; a.kn_w = e->W(blk(0, "attn.k_norm.weight")).d; }
       launch_gemm_tc(a, s);

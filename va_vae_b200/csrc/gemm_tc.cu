@@ -291,6 +291,25 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         const int rem = colc + pcc - which * D, h = rem / a.hd, d = rem - h * a.hd;
         bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)wb * a.H + h) * a.T + wt0 + prow) * a.hdp + d;
         const size_t dpass = (size_t)RPP * a.hdp;
+        if (a.rope_cs) {
+          // interleaved (cos, sin) per rotation pair: one 16-byte load covers this lane's two pairs
+          const float* cs = a.rope_cs + ((size_t)(wt0 + prow) * (a.hd >> 1) + (d >> 1)) * 2;
+          const size_t tpass = (size_t)RPP * a.hd;  // (hd/2 pairs) * 2 floats per token
+          float4 cs4[LPR];
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) cs4[ps] = *reinterpret_cast<const float4*>(cs + ps * tpass);
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) {
+            float4 v = lds128(st_r + ps * RPP * SST);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            float4 o;
+            o.x = v.x * cs4[ps].x - v.y * cs4[ps].y;
+            o.y = v.y * cs4[ps].x + v.x * cs4[ps].y;
+            o.z = v.z * cs4[ps].z - v.w * cs4[ps].w;
+            o.w = v.w * cs4[ps].z + v.z * cs4[ps].w;
+            *reinterpret_cast<uint2*>(dst + ps * dpass) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+          }
+        } else {
         const float* cp = a.cos ? a.cos + (size_t)(wt0 + prow) * a.hd + d : nullptr;
         const float* sp_ = a.cos ? a.sin + (size_t)(wt0 + prow) * a.hd + d : nullptr;
         const size_t tpass = (size_t)RPP * a.hd;
@@ -319,6 +338,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
             }
             *reinterpret_cast<uint2*>(dst + ps * dpass) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
           }
+        }
         }
       }
     }

@@ -31,6 +31,8 @@ struct TcGemmArgs {
   // qkv
   bf16 *q, *k, *vt;
   const float *cos, *sin;  // [T, hd] or null
+  const float* rope_cs;    // optional [T, hd/2, 2] interleaved (cos, sin) per rotation pair: half the table traffic;
+                           // only valid when the (T, hd) tables repeat every frequency twice (the reference's do)
   const float *qn_w, *qn_b, *kn_w, *kn_b;
   int qk_rms;
   int H, hd, hdp, hdv;
