@@ -285,3 +285,29 @@ def test_dopri5_native_vs_restated_solver(precision, tol):
     if precision == "fp32":
         assert stats["accepted"] == ref_stats["accepted"] and stats["rejected"] == ref_stats["rejected"]
         assert stats["evals"] == ref_stats["evals"]
+
+
+def test_results_do_not_depend_on_sharding_or_batch_size():
+    """the N-GPU result must equal the 1-GPU result on the same (z, y).  Emulates world sizes 2 and 8 on
+    one GPU: every shard is sampled on its own (small shards replay CUDA graphs, the full batch runs eagerly, GEMM M
+    extents differ) and the concatenation must be bit-identical to sampling the whole batch at once."""
+    import va_vae_b200 as V
+    from va_vae_b200.dist import shard_range, build_cfg_batch
+    cfg, sd, _, _ = _oracle_case("LightningDiT-S/1", 1, num_classes=31)
+    n = 131
+    z = torch.randn(n, 32, 16, 16, generator=torch.Generator().manual_seed(1234)).cuda()
+    y = torch.randint(0, 31, (n,), generator=torch.Generator().manual_seed(4321)).cuda()
+    m = _engine_model("LightningDiT-S/1", cfg, sd, "bf16")
+    eng = m.engine()
+    grid = O.time_grid(6, 0.1)
+
+    def sample(zs, ys):
+        zz, yy = build_cfg_batch(zs, ys, 31)
+        return eng.sample_ode(zz, yy, grid, "heun", True, 10.0, True, 0.11)[: zs.shape[0]]
+    whole = sample(z, y)
+    for world in (2, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            parts.append(sample(z[lo:hi], y[lo:hi]))
+        assert torch.equal(torch.cat(parts, 0), whole), f"world {world}: sharded result differs from the single-GPU result"

@@ -924,7 +924,9 @@ int gemm_tc_pick_bn(const TcGemmArgs& a) {
     VV_CHECK(best > 0, "qk-norm epilogue: no tile width <= 256 holds whole heads (head_dim must divide a multiple of 16)");
     return best;
   }
-  if (want_two_cta(a) && a.N % 256 == 0 && !(a.epi == TC_EPI_QKV && a.qn_w)) return 256;
+  if (a.N % 256 == 0 && !(a.epi == TC_EPI_QKV && a.qn_w)) return 256;
+  // The choice depends on N only - never on M: with the fused norm the per-row partial sums are grouped by column
+  // tile, so a batch-size-dependent tile width would make results depend on how samples are sharded over GPUs.
   const int cands[3] = {256, 192, 128};
   int best = 128;
   double best_eff = -1.0;
@@ -932,10 +934,6 @@ int gemm_tc_pick_bn(const TcGemmArgs& a) {
     int bn = cands[i];
     if (a.epi == TC_EPI_QKV && (a.H * a.hd) % 16 != 0) continue;
     double eff = (double)a.N / (double)(cdiv(a.N, bn) * bn);
-    // wave quantisation over the persistent grid
-    long tiles = (long)cdiv(a.M, TC_BM) * cdiv(a.N, bn);
-    long waves = (tiles + num_sms() - 1) / num_sms();
-    eff *= (double)tiles / (double)(waves * num_sms());
     // wider tiles read less shared memory per flop (B200: 128 B/clk/SM smem vs 8192 flop/clk/SM tensor)
     eff *= (bn >= 192 ? 1.0 : 0.93);
     if (eff > best_eff + 1e-9) { best_eff = eff; best = bn; }
