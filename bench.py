@@ -31,7 +31,11 @@ WORKLOADS = {
     "b1": ("LightningDiT-B/1", 31, 10.0, 0.1, 256),     # BASELINE.json configs[1] (config_dit_base.yaml)
     "xl1": ("LightningDiT-XL/1", 1000, 10.0, 0.3, 128),   # BASELINE.json configs[2]: 1024 global = 128 per GPU at 8 GPUs
     "s1": ("LightningDiT-S/1", 31, 10.0, 0.1, 4),       # BASELINE.json configs[0]
+    # BASELINE.json configs[3]: XL/1 at 512x512 = 32x32x32 latent (1024 tokens), 256 global = 32 per GPU at 8 GPUs;
+    # run with --method euler --cfg-interval-start 0.11 for the config as named
+    "xl1_512": ("LightningDiT-XL/1", 1000, 10.0, 0.3, 32),
 }
+INPUT_SIZE = {"xl1_512": 32}
 METRIC = "latent samples/sec (250-step CFG)"
 UNIT = "samples/s"
 
@@ -50,6 +54,8 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add isolated per-kernel timings to the JSON line")
+    ap.add_argument("--cfg-interval-start", type=float, default=None,
+                    help="enable the CFG interval gate (guidance only for t >= start), e.g. 0.11 for configs[3]")
     return ap.parse_args()
 
 
@@ -60,6 +66,10 @@ def peaks():
         return dict(tflops_sustained=p["bf16_tflops_sustained"], tflops_burst=p["bf16_tflops"], hbm=p["hbm_gbs"],
                     source="measured (MEASURED_PEAKS.json)")
     return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def input_size(workload):
+    return INPUT_SIZE.get(workload, 16)
 
 
 def synth_inputs(cfg, n_total, K):
@@ -126,7 +136,7 @@ def cpu_reference_rate(workload, points, method, n=4, evals=3, warm=1):
     time `evals` forward_with_cfg evaluations on n samples (2n rows) and extrapolate to the full sampler."""
     from oracle import lightningdit_oracle as O
     name, K, scale, shift, _ = WORKLOADS[workload]
-    cfg = O.config_from_name(name, input_size=16, num_classes=K)
+    cfg = O.config_from_name(name, input_size=input_size(workload), num_classes=K)
     sd = O.init_state_dict(cfg, seed=0)
     z, y = synth_inputs(cfg, n, K)
     zz, yy = torch.cat([z, z], 0), torch.cat([y, torch.full((n,), K)])
@@ -187,9 +197,10 @@ def run_engine(args):
     name, K, scale, shift, n_def = WORKLOADS[args.workload]
     n = args.n or n_def
     n_total = n * world
-    cfg = O.config_from_name(name, input_size=16, num_classes=K)
+    isz = input_size(args.workload)
+    cfg = O.config_from_name(name, input_size=isz, num_classes=K)
     sd = O.init_state_dict(cfg, seed=0)
-    model = V.LightningDiT_models[name](input_size=16, num_classes=K, in_channels=32, use_swiglu=True, use_rope=True,
+    model = V.LightningDiT_models[name](input_size=isz, num_classes=K, in_channels=32, use_swiglu=True, use_rope=True,
                                         use_rmsnorm=True, precision=args.precision, max_chunk_rows=args.chunk)
     model.load_state_dict(sd)
     model = model.eval().to(dev)
@@ -210,9 +221,11 @@ def run_engine(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    gate = dict(cfg_interval=True, cfg_interval_start=args.cfg_interval_start) if args.cfg_interval_start is not None else {}
+
     def step_resident():
         flush.zero_()
-        out = eng.sample_ode(z_dev, y_dev, grid, args.method, True, scale)
+        out = eng.sample_ode(z_dev, y_dev, grid, args.method, True, scale, **gate)
         samples = out[: hi - lo]
         if world > 1:
             gathered = torch.empty((n_total,) + tuple(samples.shape[1:]), device=dev)
@@ -222,7 +235,7 @@ def run_engine(args):
 
     def step_e2e():
         flush.zero_()
-        eng.sample_ode_host(z_pin, y_pin, grid, out_pin, args.method, True, scale)
+        eng.sample_ode_host(z_pin, y_pin, grid, out_pin, args.method, True, scale, **gate)
         return out_pin
 
     def timed(fn, k):
@@ -264,8 +277,10 @@ def run_engine(args):
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
-        config=dict(workload=f"{name} 16x16x32 latent, n={n} per GPU ({2 * n} model rows), {args.points}-point "
-                             f"{args.method}+CFG = {n_evals} evals (cfg {scale}, shift {shift}, 3 guided channels)",
+        config=dict(workload=f"{name} {isz}x{isz}x32 latent, n={n} per GPU ({2 * n} model rows), {args.points}-point "
+                             f"{args.method}+CFG = {n_evals} evals (cfg {scale}, shift {shift}, 3 guided channels"
+                             + (f", interval start {args.cfg_interval_start}: every forward executed, none skipped)"
+                                if args.cfg_interval_start is not None else ")"),
                     parallelism=f"dp{world} (samples sharded, CFG pair per GPU, one all-gather of final latents)",
                     weights="random init (oracle.init_state_dict seed 0)", l2="flushed between steps (256 MiB write)",
                     chunk_rows=args.chunk or 512, tflops_per_gpu_whole_step=achieved_total,
