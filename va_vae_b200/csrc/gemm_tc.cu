@@ -170,7 +170,14 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   const float* bvec = a.bias;
   if (fusedc) {
     float ssum = 0.f;
-    for (int pi = 0; pi < a.in_nparts; ++pi) ssum += a.in_part[(size_t)pi * a.M + wrow0 + lane];
+    // this row's partial sums are contiguous (32 slots = one 128-byte line): independent 16-byte loads, fixed order
+    const float4* pp = reinterpret_cast<const float4*>(a.in_part + (size_t)(wrow0 + lane) * 32);
+    const int np4 = (a.in_nparts + 3) >> 2;
+    float4 pv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pv[i] = i < np4 ? pp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ssum += ((pv[i].x + pv[i].y) + pv[i].z) + pv[i].w;
     in_rstd = rsqrtf(ssum / (float)a.in_dim + 1e-6f);
     bvec = a.sp + (size_t)wb * a.sp_ld;
   }
@@ -200,6 +207,18 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
     }
   };
   prefetch(half);
+  // consumer epilogues: the per-sample shift.W^T+bias vector lives in the big `mod` matrix (DRAM latency): request
+  // the vectors of all (<= 4) chunks this warp will process before waiting for the accumulator
+  constexpr bool kBiasAhead = EPI == TC_EPI_SWIGLU || EPI == TC_EPI_EMBED;  // (QKV: register budget, stays one-ahead)
+  float4 bball[4];
+  if (kBiasAhead) {
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      const int c = half + 2 * ci;
+      bball[ci] = (bvec && c < n_chunks) ? *reinterpret_cast<const float4*>(bvec + n0 + c * CW + pcc)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   float ssacc[LPR];
 #pragma unroll
   for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
@@ -207,7 +226,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   ptx::mbar_wait(tfull, aphase);
   ptx::tc_fence_after();
 
-  for (int c = half; c < n_chunks; c += 2) {
+  auto chunk_body = [&](const int c, const float4 bb_ahead) {
     const int c0 = c * CW;
     uint32_t r[CW];
     ptx::tmem_ld_x32(tbase + c0, r);
@@ -216,8 +235,8 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
 #pragma unroll
       for (int ps = 0; ps < LPR; ++ps) xcur[ps] = xpre[ps];
     }
-    const float4 bb = bb_n, g1 = g_n, cw = cw_n;
-    prefetch(c + 2);
+    const float4 bb = kBiasAhead ? bb_ahead : bb_n, g1 = g_n, cw = cw_n;
+    if (!kBiasAhead) prefetch(c + 2);
     ptx::tmem_ld_wait();
 
     // stage the 32 x 32 fp32 block (thread == row), scaled by 1/rms when the norm is fused
@@ -342,6 +361,15 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         }
       }
     }
+  };
+  if (kBiasAhead) {
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      const int c = half + 2 * ci;
+      if (c < n_chunks) chunk_body(c, bball[ci]);
+    }
+  } else {
+    for (int c = half; c < n_chunks; c += 2) chunk_body(c, make_float4(0.f, 0.f, 0.f, 0.f));
   }
   if (EPI == TC_EPI_GATED_RESIDUAL && a.nx_w) {
 #pragma unroll
@@ -350,7 +378,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
       v += __shfl_xor_sync(0xffffffffu, v, 4);
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 1);
-      if ((lane & 7) == 0) a.nx_part[(size_t)(n_blk * 2 + half) * a.M + wrow0 + ps * RPP + prow] = v;
+      if ((lane & 7) == 0) a.nx_part[(size_t)(wrow0 + ps * RPP + prow) * 32 + (n_blk * 2 + half)] = v;
     }
   }
 }
@@ -597,7 +625,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part) {
         float ssum = 0.f;
         if (my_row < a.M)
-          for (int pi = 0; pi < a.in_nparts; ++pi) ssum += a.in_part[(size_t)pi * a.M + my_row];
+        {
+          const float4* pp = reinterpret_cast<const float4*>(a.in_part + (size_t)my_row * 32);
+          const int np4 = (a.in_nparts + 3) >> 2;
+          for (int i = 0; i < np4; ++i) {
+            const float4 pv = pp[i];
+            ssum += ((pv.x + pv.y) + pv.z) + pv.w;
+          }
+        }
         in_rstd = rsqrtf(ssum / (float)a.in_dim + 1e-6f);
       }
       // per-row bias source: per-sample vector sp[b,:] when the norm is fused, else the plain bias
@@ -864,7 +899,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
           const int row = wrow0 + ps * RPP + prow;
-          if ((lane % LPR) == 0 && row < a.M) a.nx_part[(size_t)(n_blk * 2 + half) * a.M + row] = v;
+          if ((lane % LPR) == 0 && row < a.M) a.nx_part[(size_t)row * 32 + (n_blk * 2 + half)] = v;
         }
       }
       // release this accumulator stage to the MMA warp
