@@ -152,6 +152,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();   // q / k / v^T of the preceding QKV GEMM are read from here on
 
   if (warp == 4) {
     // ------------------------------------------------------------- control thread: TMA + MMA issue
@@ -508,8 +510,22 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
     VV_CUDA(cudaFuncSetAttribute(k_attention_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (multi) k_attention_tc<true><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, tmQt, tmKt, a);
-  else k_attention_tc<false><<<grid, AT_THREADS, smem, s>>>(tmQ, tmK, tmV, tmQt, tmKt, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(AT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled(s)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (multi) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<true>, tmQ, tmK, tmV, tmQt, tmKt, a));
+  else VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<false>, tmQ, tmK, tmV, tmQt, tmKt, a));
   VV_LAUNCH_CHECK();
 }
 

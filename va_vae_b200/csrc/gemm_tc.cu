@@ -10,6 +10,7 @@
 #include "tc_ptx.cuh"
 
 #include <mutex>
+#include <cstdlib>
 
 namespace vv {
 
@@ -504,6 +505,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (TWO) ptx2::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // everything above overlapped the predecessor's tail (PDL); from here on its outputs are read
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -918,6 +922,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // ------------------------------------------------------------------------------------------------ host launch
+// Programmatic dependent launch for the tcgen05 kernels: opt-in with VAVAE_PDL=1 (an A/B on B200 showed no gain at the
+// benchmark batch sizes: 858-861 TFLOP/s either way, the persistent kernels' tails are short); never used while a
+// stream is being captured into a CUDA graph.
+bool pdl_enabled(cudaStream_t s) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = std::getenv("VAVAE_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!on) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st == cudaStreamCaptureStatusNone;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (!g_num_sms) {
@@ -996,25 +1015,34 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
   }
   CUtensorMap tmA = make_tmap_2d_bf16(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, TC_BK, TC_BM);
   CUtensorMap tmB = make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK, (uint32_t)b_rows);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled(s)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if (!TWO) {
     const int tiles = cdiv(a.M, TC_BM) * cdiv(a.N, BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    k_gemm_tc<EPI, CW, false><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, a, BN, nstages);
+    cfg.gridDim = dim3(tiles < num_sms() ? tiles : num_sms());
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, false>, tmA, tmB, a, BN, nstages));
   } else {
     const int tiles = cdiv(a.M, 2 * TC_BM) * cdiv(a.N, BN);
     const int pairs = std::min(tiles, num_sms() / 2);
-    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, true>, tmA, tmB, a, BN, nstages));
   }
   VV_LAUNCH_CHECK();

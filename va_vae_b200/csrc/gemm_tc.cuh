@@ -70,6 +70,7 @@ struct TcAttnArgs {
   int B, H, T, hd, hdp, hdv;
 };
 void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s);
+bool pdl_enabled(cudaStream_t s);
 // rows of the transposed V tensor: head_dim + one row of ones (row-sum column of P V), rounded up to 16
 int attention_hdv(int hd);
 
