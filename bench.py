@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="add isolated per-kernel timings to the JSON line")
+    ap.add_argument("--profile-kernel", default="gemm_w12",
+                    choices=["gemm_qkv", "attention", "gemm_proj", "gemm_w12", "gemm_w3", "norm_modulate", "ode_update"],
+                    help="kernel class bracketed by CUDA events inside the timed region (roofline object)")
     ap.add_argument("--cfg-interval-start", type=float, default=None,
                     help="enable the CFG interval gate (guidance only for t >= start), e.g. 0.11 for configs[3]")
     return ap.parse_args()
@@ -255,7 +258,7 @@ def run_engine(args):
         step_resident()
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = eng.launch_count
-    eng.profile_begin("gemm_w12")
+    eng.profile_begin(args.profile_kernel)
     ms = timed(step_resident, args.steps)
     prof_ms, prof_n, prof_work = eng.profile_end()
     launches = torch.tensor([eng.launch_count - l0], device=dev, dtype=torch.int64)
@@ -272,7 +275,12 @@ def run_engine(args):
     pk = peaks()
     flops_fwd = O.flops_per_forward(cfg)
     achieved_total = value * flops_fwd * 2 * n_evals / 1e12 / world      # per-GPU TFLOP/s over the whole step
-    roof_achieved = prof_work / (prof_ms / 1e3) / 1e12 if prof_ms > 0 else None
+    hbm_kernel = args.profile_kernel in ("norm_modulate", "ode_update")
+    roof_achieved = prof_work / (prof_ms / 1e3) / (1e9 if hbm_kernel else 1e12) if prof_ms > 0 else None
+    roof_peak = pk["hbm"] if hbm_kernel else pk["tflops_sustained"]
+    kernel_names = {"gemm_w12": "k_gemm_tc<SWIGLU> (mlp.w12, 42.8% of FLOPs)", "gemm_qkv": "k_gemm_tc<QKV> (attn.qkv + RoPE + scatter)",
+                    "gemm_proj": "k_gemm_tc<GATED_RESIDUAL> (attn.proj)", "gemm_w3": "k_gemm_tc<GATED_RESIDUAL> (mlp.w3)",
+                    "attention": "k_attention_tc", "norm_modulate": "k_norm_modulate", "ode_update": "k_ode_update"}
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -290,12 +298,13 @@ def run_engine(args):
                  d2h_bytes_per_step=int(zz.numel() * 4) * world, steps=k_e2e,
                  api="Engine.sample_ode_host -> vavae_sample_ode_host (pinned host buffers)"),
         gpu_launches=int(launches.item()),
-        roofline=dict(bound="tensor", kernel="k_gemm_tc<SWIGLU> (mlp.w12, 42.8% of FLOPs)", achieved=roof_achieved,
-                      peak=pk["tflops_sustained"], unit="TFLOP/s",
-                      frac=(roof_achieved / pk["tflops_sustained"]) if roof_achieved else None,
+        roofline=dict(bound="hbm" if hbm_kernel else "tensor", kernel=kernel_names[args.profile_kernel], achieved=roof_achieved,
+                      peak=roof_peak, unit="GB/s" if hbm_kernel else "TFLOP/s",
+                      frac=(roof_achieved / roof_peak) if roof_achieved else None,
                       # dram__bytes_read+write per launch from profiles/r1_w12_ncu.md (B/1, 512-row chunks) vs
                       # 744.5e6 algorithmic bytes; only valid for that exact launch shape
-                      traffic=(710.9e6 if (args.workload == "b1" and 2 * n >= 512 and not args.chunk) else None),
+                      traffic=(710.9e6 if (args.workload == "b1" and 2 * n >= 512 and not args.chunk
+                                           and args.profile_kernel == "gemm_w12") else None),
                       launches_timed=prof_n, peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)"),
     )
     if args.breakdown and rank == 0:
