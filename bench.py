@@ -303,7 +303,7 @@ def run_engine(args):
                       frac=(roof_achieved / roof_peak) if roof_achieved else None,
                       # dram__bytes_read+write per launch from profiles/r1_w12_ncu.md (B/1, 512-row chunks) vs
                       # 744.5e6 algorithmic bytes; only valid for that exact launch shape
-                      traffic=(710.9e6 if (args.workload == "b1" and 2 * n >= 512 and not args.chunk
+                      traffic=(728.1e6 if (args.workload == "b1" and 2 * n >= 512 and not args.chunk
                                            and args.profile_kernel == "gemm_w12") else None),
                       launches_timed=prof_n, peak_source=pk["source"] + ", sustained figure (kernel timed inside a long step)"),
     )
