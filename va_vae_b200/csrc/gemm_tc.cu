@@ -191,7 +191,9 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   }
   const size_t xpass = (size_t)RPP * a.ldo;  // elements between passes
   float4 xpre[LPR];
-  float4 bb_n = make_float4(0.f, 0.f, 0.f, 0.f), g_n = bb_n, cw_n = bb_n;
+  // prefetched one chunk ahead: bias, gate, and the RAW weight / scale vectors of the norm that follows (they are
+  // combined at the point of use - combining them here would stall the warp on its own loads)
+  float4 bb_n = make_float4(0.f, 0.f, 0.f, 0.f), g_n = bb_n, nw_n = bb_n, ns_n = bb_n;
   auto prefetch = [&](int c) {
     if (c >= n_chunks) return;
     const int colv = n0 + c * CW + pcc;
@@ -201,9 +203,8 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
       for (int ps = 0; ps < LPR; ++ps) xpre[ps] = *reinterpret_cast<const float4*>(xptr + ps * xpass + c * CW);
       g_n = *reinterpret_cast<const float4*>(modrow + a.gate_off + colv);
       if (a.nx_w) {
-        const float4 w4 = *reinterpret_cast<const float4*>(a.nx_w + colv);
-        const float4 s4 = *reinterpret_cast<const float4*>(modrow + a.nx_scale_off + colv);
-        cw_n = make_float4(w4.x * (1.f + s4.x), w4.y * (1.f + s4.y), w4.z * (1.f + s4.z), w4.w * (1.f + s4.w));
+        nw_n = *reinterpret_cast<const float4*>(a.nx_w + colv);
+        ns_n = *reinterpret_cast<const float4*>(modrow + a.nx_scale_off + colv);
       }
     }
   };
@@ -224,6 +225,29 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
 #pragma unroll
   for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
 
+  // QKV: head index / in-head offset by multiply-high (exact for col * hd < 2^32) instead of integer division, and
+  // the interleaved RoPE table rows of this lane kept in registers, (re)loaded at the end of the previous chunk and
+  // only when the in-head offset changes (head_dim 64: a warp sees the same offsets in every q/k chunk of a tile)
+  const int qD = EPI == TC_EPI_QKV ? a.H * a.hd : 1;
+  const uint32_t hd_magic = EPI == TC_EPI_QKV ? 0xFFFFFFFFu / (uint32_t)a.hd + 1u : 0u;
+  float4 cs_n[LPR];
+  int cs_key = -1;
+  auto prefetch_cs = [&](int c) {
+    if (c >= n_chunks) return;
+    const int colc = n0 + c * CW;
+    const int which = (colc >= qD) + (colc >= 2 * qD);
+    if (which == 2) return;
+    const int rem = colc + pcc - which * qD;
+    const int d = rem - (int)__umulhi((uint32_t)rem, hd_magic) * a.hd;
+    if (d == cs_key) return;
+    cs_key = d;
+    const float* cs = a.rope_cs + ((size_t)(wt0 + prow) * (a.hd >> 1) + (d >> 1)) * 2;
+    const size_t tpass = (size_t)RPP * a.hd;  // (hd/2 pairs) * 2 floats per token
+#pragma unroll
+    for (int ps = 0; ps < LPR; ++ps) cs_n[ps] = *reinterpret_cast<const float4*>(cs + ps * tpass);
+  };
+  if (EPI == TC_EPI_QKV && a.rope_cs) prefetch_cs(half);
+
   ptx::mbar_wait(tfull, aphase);
   ptx::tc_fence_after();
 
@@ -236,7 +260,9 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
 #pragma unroll
       for (int ps = 0; ps < LPR; ++ps) xcur[ps] = xpre[ps];
     }
-    const float4 bb = kBiasAhead ? bb_ahead : bb_n, g1 = g_n, cw = cw_n;
+    const float4 bb = kBiasAhead ? bb_ahead : bb_n, g1 = g_n;
+    const float4 cw = make_float4(nw_n.x * (1.f + ns_n.x), nw_n.y * (1.f + ns_n.y), nw_n.z * (1.f + ns_n.z),
+                                  nw_n.w * (1.f + ns_n.w));
     if (!kBiasAhead) prefetch(c + 2);
     ptx::tmem_ld_wait();
 
@@ -286,47 +312,52 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         *reinterpret_cast<uint32_t*>(ho + ps * hpass) = pack_bf16(silu_fast(v.x) * v.y, silu_fast(v.z) * v.w);
       }
     } else if (EPI == TC_EPI_QKV) {
-      const int D = a.H * a.hd;
+      const int D = qD;
       const int colc = n0 + c0;
-      const int which = colc / D;  // chunk-uniform: D % 32 == 0
+      const int which = (colc >= D) + (colc >= 2 * D);  // chunk-uniform: D % 32 == 0
       if (which == 2) {
-        // V^T: lane owns head-dim column j and 8 consecutive tokens -> one 16-byte store of (B,H,hdv,T)
+        // V^T: lane owns head-dim column j and 8 consecutive tokens -> one 16-byte store of (B,H,hdv,T).
+        // Column reads of the staging block: rows 8 apart share banks, so the four token groups of a warp walk
+        // their 8 tokens in rotated order (group tg starts at token 2*tg) and the packed pairs are rotated back.
         const int tg = lane & 3;
+        uint32_t ro[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ro[e] = (uint32_t)(((e + 2 * tg) & 7) * SST);
         float bv4[4];
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) bv4[ps] = bvec[colc + ps * 8 + (lane >> 2)];
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) {
           const int j = ps * 8 + (lane >> 2);
-          const int rem = colc + j - 2 * D, h = rem / a.hd, d = rem - h * a.hd;
+          const int rem = colc + j - 2 * D, h = (int)__umulhi((uint32_t)rem, hd_magic), d = rem - h * a.hd;
           const uint32_t sa = st_s + (uint32_t)(tg * 8) * SST + j * 4;
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = lds32(sa + e * SST) + bv4[ps];
+          for (int e = 0; e < 8; ++e) f[e] = lds32(sa + ro[e]) + bv4[ps];
+          // pr[i] holds tokens 2*((i + tg) & 3), +1 ; wanted: pk[k] = tokens 2k, 2k+1 = pr[(k - tg) & 3]
+          const uint32_t pr0 = pack_bf16(f[0], f[1]), pr1 = pack_bf16(f[2], f[3]), pr2 = pack_bf16(f[4], f[5]),
+                         pr3 = pack_bf16(f[6], f[7]);
+          const bool r1 = tg & 1, r2 = tg & 2;
+          const uint32_t q0 = r1 ? pr3 : pr0, q1 = r1 ? pr0 : pr1, q2 = r1 ? pr1 : pr2, q3 = r1 ? pr2 : pr3;
           *reinterpret_cast<uint4*>(a.vt + (((size_t)wb * a.H + h) * a.hdv + d) * a.T + wt0 + tg * 8) =
-              make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+              make_uint4(r2 ? q2 : q0, r2 ? q3 : q1, r2 ? q0 : q2, r2 ? q1 : q3);
         }
       } else {
-        // q / k: bias, RoPE (pos_embed.py:38-42,135), head-major store; all table loads before the first store
-        const int rem = colc + pcc - which * D, h = rem / a.hd, d = rem - h * a.hd;
+        // q / k: bias, RoPE (pos_embed.py:38-42,135), head-major store
+        const int rem = colc + pcc - which * D, h = (int)__umulhi((uint32_t)rem, hd_magic), d = rem - h * a.hd;
         bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)wb * a.H + h) * a.T + wt0 + prow) * a.hdp + d;
         const size_t dpass = (size_t)RPP * a.hdp;
         if (a.rope_cs) {
-          // interleaved (cos, sin) per rotation pair: one 16-byte load covers this lane's two pairs
-          const float* cs = a.rope_cs + ((size_t)(wt0 + prow) * (a.hd >> 1) + (d >> 1)) * 2;
-          const size_t tpass = (size_t)RPP * a.hd;  // (hd/2 pairs) * 2 floats per token
-          float4 cs4[LPR];
-#pragma unroll
-          for (int ps = 0; ps < LPR; ++ps) cs4[ps] = *reinterpret_cast<const float4*>(cs + ps * tpass);
+          // interleaved (cos, sin) per rotation pair, held in cs_n (see prefetch_cs)
 #pragma unroll
           for (int ps = 0; ps < LPR; ++ps) {
             float4 v = lds128(st_r + ps * RPP * SST);
             v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
             float4 o;
-            o.x = v.x * cs4[ps].x - v.y * cs4[ps].y;
-            o.y = v.y * cs4[ps].x + v.x * cs4[ps].y;
-            o.z = v.z * cs4[ps].z - v.w * cs4[ps].w;
-            o.w = v.w * cs4[ps].z + v.z * cs4[ps].w;
+            o.x = v.x * cs_n[ps].x - v.y * cs_n[ps].y;
+            o.y = v.y * cs_n[ps].x + v.x * cs_n[ps].y;
+            o.z = v.z * cs_n[ps].z - v.w * cs_n[ps].w;
+            o.w = v.w * cs_n[ps].z + v.z * cs_n[ps].w;
             *reinterpret_cast<uint2*>(dst + ps * dpass) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
           }
         } else {
@@ -361,6 +392,8 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         }
         }
       }
+      // table rows of this warp's next q/k chunk (a no-op while the in-head offset stays the same)
+      if (a.rope_cs) prefetch_cs(c + 2);
     }
   };
   if (kBiasAhead) {

@@ -13,7 +13,8 @@ from typing import Dict, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvavae_b200.so")
+# VAVAE_B200_LIB: developer knob for same-box A/B runs of two builds of the library (tools/ab_gemms.py)
+LIB_PATH = os.environ.get("VAVAE_B200_LIB") or os.path.join(_HERE, "libvavae_b200.so")
 
 PREC_BF16, PREC_FP32 = 0, 1
 ODE_EULER, ODE_HEUN = 0, 1
