@@ -1,10 +1,11 @@
 #!/bin/bash
 # Same-box A/B of several builds of the library: tools/ab/<name>.so (built by hand, git-ignored).
-# usage: tools/ab_libs.sh name1 name2 ...   (each variant: isolated GEMM table, then a 16-point bench)
+# usage: tools/ab_libs.sh <script.py> name1 name2 ...   then a 16-point bench per variant
+script=$1; shift
 for rep in 1 2; do
   for v in "$@"; do
     echo "== $v (rep $rep)"
-    VAVAE_B200_LIB=$PWD/tools/ab/$v.so timeout -s KILL 200 python tools/ab_gemms.py 2>&1 | grep -v attention | tail -8
+    VAVAE_B200_LIB=$PWD/tools/ab/$v.so timeout -s KILL 200 python $script 2>&1 | tail -8
   done
 done
 for rep in 1 2; do
