@@ -114,11 +114,14 @@ __host__ __device__ inline AtGeom at_geom(int hdp, int hdv) {
   return g;
 }
 
-template <bool MULTI>
+// OACC: fp32 output columns a thread accumulates in registers across key blocks (0: single-block items, O goes
+// straight from TMEM to global; 80: head_dim <= 79 - every registry model; 128: up to head_dim 112)
+template <int OACC>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQt,
                const __grid_constant__ CUtensorMap tmKt, const TcAttnArgs a) {
+  constexpr bool MULTI = OACC > 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const AtGeom g = at_geom(a.hdp, a.hdv);
@@ -251,9 +254,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int bh = item / nq, q0 = (item % nq) * AT_BQ;
       float m_run = -INFINITY;
-      float oacc[MULTI ? 128 : 1];
+      float oacc[MULTI ? OACC : 1];
 #pragma unroll
-      for (int i = 0; i < (MULTI ? 128 : 1); ++i) oacc[i] = 0.f;
+      for (int i = 0; i < (MULTI ? OACC : 1); ++i) oacc[i] = 0.f;
 
       for (int blk = 0; blk < nblk; ++blk, ++step) {
         const uint32_t ph = step & 1;
@@ -426,7 +429,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ptx::tmem_ld_wait();
             // oacc is only ever indexed with compile-time constants (fully unrolled, guarded by c0)
 #pragma unroll
-            for (int cc = 0; cc < (MULTI ? 8 : 0); ++cc) {
+            for (int cc = 0; cc < OACC / 16; ++cc) {
               if (c0 == cc * 16) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) oacc[cc * 16 + j] = oacc[cc * 16 + j] * alpha + __uint_as_float(r[j]);
@@ -438,14 +441,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (last) {
             float l = 0.f;
 #pragma unroll
-            for (int i = 0; i < (MULTI ? 128 : 0); ++i)
+            for (int i = 0; i < OACC; ++i)
               if (i == a.hd) l = oacc[i];
             const float inv = 1.0f / l;
             const int b = bh / a.H, h = bh % a.H;
             const bool valid = (q0 + row) < a.T;
             bf16* orow = a.out + ((size_t)b * a.T + q0 + row) * ((size_t)a.H * a.hd) + (size_t)h * a.hd;
 #pragma unroll
-            for (int c8 = 0; c8 < (MULTI ? 16 : 0); ++c8) {
+            for (int c8 = 0; c8 < OACC / 8; ++c8) {
               if (c8 * 8 < a.hd && valid) {
                 uint4 pk;
                 __nv_bfloat162 t0 = __floats2bfloat162_rn(oacc[c8 * 8 + 0] * inv, oacc[c8 * 8 + 1] * inv);
@@ -511,8 +514,9 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   const bool multi = a.T > AT_BKV;
   static bool attr_set = false;   // not a stream operation: done once, outside any graph capture
   if (!attr_set) {
-    VV_CUDA(cudaFuncSetAttribute(k_attention_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    VV_CUDA(cudaFuncSetAttribute(k_attention_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VV_CUDA(cudaFuncSetAttribute(k_attention_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VV_CUDA(cudaFuncSetAttribute(k_attention_tc<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VV_CUDA(cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -529,8 +533,9 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (multi) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<true>, tmQ, tmK, tmV, tmQt, tmKt, a));
-  else VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<false>, tmQ, tmK, tmV, tmQt, tmKt, a));
+  if (multi && a.hd + 1 <= 80) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<80>, tmQ, tmK, tmV, tmQt, tmKt, a));
+  else if (multi) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<128>, tmQ, tmK, tmV, tmQt, tmKt, a));
+  else VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<0>, tmQ, tmK, tmV, tmQt, tmKt, a));
   VV_LAUNCH_CHECK();
 }
 
