@@ -147,6 +147,44 @@ int vavae_set_gemm_two_cta(int on);
 int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work,
                       void* stream);
 
+/* ===== VA-VAE decode path =====================================================
+ * Replaces, for inference, AutoencoderKL.decode (LightningDiT/tokenizer/autoencoder.py:490-493: post_quant_conv ->
+ * Decoder, :277-399) and the caller-side post-processing of VA_VAE.decode_to_images (LightningDiT/tokenizer/
+ * vavae.py:72-82: clamp(127.5 x + 128, 0, 255) -> uint8 NHWC).  Weights are loaded under the reference's
+ * state_dict names ("post_quant_conv.weight", "decoder.conv_in.weight", "decoder.up.3.block.0.nin_shortcut.bias",
+ * ...), fp32, PyTorch layouts. */
+typedef struct vavae_decoder vavae_decoder_t;
+
+typedef struct vavae_decoder_config {
+  int32_t abi_version;     /* must be VAVAE_ABI_VERSION */
+  int32_t z_channels;      /* embed_dim = 32, tokenizer/configs/vavae_f16d32.yaml:8,28 */
+  int32_t ch;              /* 128 */
+  int32_t num_levels;      /* len(ch_mult), 5 */
+  int32_t ch_mult[8];      /* (1, 1, 2, 2, 4) */
+  int32_t num_res_blocks;  /* 2 (the decoder runs num_res_blocks + 1 blocks per level, autoencoder.py:343) */
+  int32_t num_attn_res;    /* number of entries of attn_res */
+  int32_t attn_res[4];     /* resolutions with attention blocks, (16) */
+  int32_t resolution;      /* output height = width, 256 */
+  int32_t out_ch;          /* 3 */
+  int32_t precision;       /* 0: bf16 tensor-core path (fp32 accumulate, fp32 residual stream); 1: fp32 SIMT validation */
+  int32_t max_batch;       /* images decoded per pass (workspace size); 0 = default (8) */
+} vavae_decoder_config_t;
+
+/* Same conventions as the sampler engine: 0 / non-zero return, vavae_last_error() for the message, no CPU fallback. */
+int vavae_decoder_create(const vavae_decoder_config_t* cfg, int device, vavae_decoder_t** out);
+int vavae_decoder_destroy(vavae_decoder_t* d);
+/* One call per state_dict entry the decode path reads (oracle/vavae_decoder_oracle.py:state_dict_spec lists them). */
+int vavae_decoder_load_weight(vavae_decoder_t* d, const char* name, const float* data, const int64_t* shape, int ndim,
+                              int is_device);
+/* Validates shapes, packs tap-major bf16 convolution weights, allocates the workspace. */
+int vavae_decoder_finalize(vavae_decoder_t* d);
+/* z: device fp32 (n, z_channels, r, r) NCHW latents, already de-normalised (inference.py:220).  Writes either or both
+ * of out_nchw: device fp32 (n, out_ch, R, R) = AutoencoderKL.decode(z), and out_u8_nhwc: device uint8 (n, R, R, out_ch)
+ * = VA_VAE.decode_to_images(z).  Enqueued on `stream`, no synchronisation. */
+int vavae_decoder_decode(vavae_decoder_t* d, const float* z, int n, float* out_nchw, uint8_t* out_u8_nhwc, void* stream);
+uint64_t vavae_decoder_launch_count(vavae_decoder_t* d);
+uint64_t vavae_decoder_device_bytes(vavae_decoder_t* d);
+
 #ifdef __cplusplus
 }
 #endif

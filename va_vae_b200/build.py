@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libvavae_b200.so")
-SOURCES = ["kernels_bw.cu", "gemm_f32.cu", "gemm_tc.cu", "attn_tc.cu", "engine.cu"]
+SOURCES = ["kernels_bw.cu", "gemm_f32.cu", "gemm_tc.cu", "attn_tc.cu", "engine.cu", "decoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

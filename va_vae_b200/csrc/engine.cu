@@ -16,7 +16,8 @@
 
 using namespace vv;
 
-static thread_local std::string g_err;
+thread_local std::string vv_last_error_buf;   // shared with decoder.cu
+#define g_err vv_last_error_buf
 
 struct Weight {
   float* d = nullptr;

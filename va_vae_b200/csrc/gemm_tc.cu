@@ -62,6 +62,22 @@ CUtensorMap make_tmap_3d_bf16(const void* base, uint64_t d0, uint64_t d1, uint64
   return m;
 }
 
+CUtensorMap make_tmap_nhwc_bf16(const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t bw,
+                                uint32_t bh, uint32_t bn) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * 2, C * W * 2, C * W * H * 2};
+  cuuint32_t box[4] = {64, bw, bh, bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  VV_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 64 == 0, "NHWC tensor map: base alignment / channels % 64");
+  VV_CHECK(bw <= 256 && bh <= 256 && bn <= 256 && bw * bh * bn == 128, "NHWC tensor map: box must cover 128 pixels");
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // out-of-bounds elements read as zero = the conv padding
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(nhwc) failed with code " + std::to_string((int)r));
+  return m;
+}
+
 CUtensorMap make_tmap_3d_bf16_sw(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                                  uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes) {
   CUtensorMap m;
@@ -443,6 +459,15 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3) {
+  const uint32_t bar_leader = ptx::smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_result)),
                "r"(ncols)
@@ -549,18 +574,39 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t phase = 0;
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int a_row0 = m_blk * tile_m + (int)rank * TC_BM;   // first A row (= output pixel) of this CTA's tile
+        // implicit-GEMM convolution: the tile is 128 consecutive pixels of one image (a row segment when W >= 128,
+        // 128 / W whole rows otherwise); tap (dy, dx) shifts the box, TMA zero-fills what falls outside the image
+        int cv_n = 0, cv_h = 0, cv_w = 0, cv_cpb = 1;
+        if (a.conv_taps) {
+          const int hw = a.conv_H * a.conv_W;
+          cv_n = a_row0 / hw;
+          const int rem = a_row0 - cv_n * hw;
+          cv_h = rem / a.conv_W;
+          cv_w = rem - cv_h * a.conv_W;
+          cv_cpb = a.lda / TC_BK;
+        }
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + TC_A_BYTES;
+          int tap = 0, cb = kb;
+          if (a.conv_taps) { tap = kb / cv_cpb; cb = kb - tap * cv_cpb; }
+          const int dy = a.conv_taps == 9 ? tap / 3 - 1 : 0, dx = a.conv_taps == 9 ? tap % 3 - 1 : 0;
           if (TWO) {
             // both CTAs' bytes are credited to the leader's barrier; only the leader arms it (with the pair's total)
             if (rank == 0) ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * stage_bytes));
-            ptx2::tma_load_2d_2sm(sa, &tmA, &bars->full[stage], kb * TC_BK, m_blk * tile_m + (int)rank * TC_BM);
+            if (a.conv_taps)
+              ptx2::tma_load_4d_2sm(sa, &tmA, &bars->full[stage], cb * TC_BK, cv_w + dx, cv_h + dy, cv_n);
+            else
+              ptx2::tma_load_2d_2sm(sa, &tmA, &bars->full[stage], kb * TC_BK, a_row0);
             ptx2::tma_load_2d_2sm(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN + (int)rank * b_rows);
           } else {
             ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
-            ptx::tma_load_2d(sa, &tmA, &bars->full[stage], kb * TC_BK, m_blk * TC_BM);
+            if (a.conv_taps)
+              ptx::tma_load_4d(sa, &tmA, &bars->full[stage], cb * TC_BK, cv_w + dx, cv_h + dy, cv_n);
+            else
+              ptx::tma_load_2d(sa, &tmA, &bars->full[stage], kb * TC_BK, a_row0);
             ptx::tma_load_2d(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN);
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -914,6 +960,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = v;
           } else if (EPI == TC_EPI_BIAS_F32) {
+            if (a.res) {
+              const float4 r4 = *reinterpret_cast<const float4*>(a.res + (size_t)row * a.ldo + col);
+              v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+            }
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = v;
           } else if (EPI == TC_EPI_BIAS_BF16 || EPI == TC_EPI_GELU_BF16) {
             if (EPI == TC_EPI_GELU_BF16) {
@@ -1046,7 +1096,16 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
     VV_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, CW, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  CUtensorMap tmA = make_tmap_2d_bf16(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, TC_BK, TC_BM);
+  CUtensorMap tmA;
+  if (a.conv_taps) {
+    // 128 consecutive pixels: a row segment (W >= 128), whole rows (W < 128 <= H*W) or whole images (H*W < 128)
+    const uint32_t bw = a.conv_W >= 128 ? 128u : (uint32_t)a.conv_W;
+    const uint32_t bh = std::min<uint32_t>((uint32_t)a.conv_H, 128u / bw);
+    tmA = make_tmap_nhwc_bf16(a.A, (uint64_t)a.lda, (uint64_t)a.conv_W, (uint64_t)a.conv_H,
+                              (uint64_t)(a.M / (a.conv_H * a.conv_W)), bw, bh, 128u / (bw * bh));
+  } else {
+    tmA = make_tmap_2d_bf16(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, TC_BK, TC_BM);
+  }
   CUtensorMap tmB = make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK, (uint32_t)b_rows);
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(TC_THREADS);
@@ -1098,6 +1157,14 @@ static void launch_epi(const TcGemmArgs& a, int BN, int cw, cudaStream_t s) {
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   VV_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tc: empty problem");
   VV_CHECK(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm_tc: row pitch must be a multiple of 8 bf16 (16 bytes)");
+  if (a.conv_taps) {
+    VV_CHECK(a.conv_taps == 1 || a.conv_taps == 9, "gemm_tc: convolution taps must be 1 or 9");
+    VV_CHECK(a.lda % TC_BK == 0 && a.K == a.conv_taps * a.lda, "gemm_tc: conv channels % 64 and K = taps * channels");
+    const int hw = a.conv_H * a.conv_W;
+    VV_CHECK((hw % TC_BM == 0 || TC_BM % hw == 0) && a.M % hw == 0, "gemm_tc: conv image size must divide or be a multiple of 128 pixels");
+    VV_CHECK(a.conv_W >= 128 ? a.conv_W % 128 == 0 : 128 % a.conv_W == 0, "gemm_tc: conv width must divide or be a multiple of 128");
+  }
+  VV_CHECK(a.res == nullptr || a.epi == TC_EPI_BIAS_F32, "gemm_tc: residual input only with the fp32 bias epilogue");
   const int BN = gemm_tc_pick_bn(a);
   int cw = (BN % 32 == 0) ? 32 : 16;
   if (a.epi == TC_EPI_QKV && (a.H * a.hd) % 32 != 0) cw = 16;

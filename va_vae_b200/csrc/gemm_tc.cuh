@@ -55,6 +55,13 @@ struct TcGemmArgs {
   int in_nparts, in_dim;
   const float* sp;
   int sp_ld;
+  // ---- implicit-GEMM convolution (VA-VAE decoder): A is an NHWC bf16 activation tensor (N_img, H, W, lda channels,
+  // lda % 64 == 0) read through a 4-D tensor map; K = conv_taps * lda with tap-major weights [N][tap][lda]; tap t
+  // of a 3x3 kernel reads pixel (h + t/3 - 1, w + t%3 - 1), out-of-image pixels are zero-filled by TMA.
+  // M = N_img*H*W (H*W % 128 == 0).  conv_taps: 0 = plain GEMM, 1 = 1x1, 9 = 3x3 (stride 1, padding 1).
+  int conv_taps, conv_H, conv_W;
+  // TC_EPI_BIAS_F32 only: optional fp32 residual [M, ldo] added to acc + bias (may alias `out`)
+  const float* res;
 };
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);

@@ -72,6 +72,15 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
@@ -164,5 +173,8 @@ CUtensorMap make_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, 
                               uint32_t box_inner, uint32_t box_outer);
 CUtensorMap make_tmap_3d_bf16(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                               uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
+// NHWC activation tensor (C innermost, densely packed) for the implicit-GEMM convolution: box = 64 channels x bw x bh x bn
+CUtensorMap make_tmap_nhwc_bf16(const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t bw,
+                                uint32_t bh, uint32_t bn);
 
 }  // namespace vv

@@ -25,6 +25,8 @@ EXPORTS = [
     "vavae_forward", "vavae_forward_with_cfg", "vavae_sample_ode", "vavae_sample_ode_host", "vavae_launch_count",
     "vavae_device_bytes", "vavae_test_gemm_bf16", "vavae_test_attention_bf16", "vavae_time_kernel",
     "vavae_profile_begin", "vavae_profile_end", "vavae_set_gemm_two_cta", "vavae_sample_dopri5",
+    "vavae_decoder_create", "vavae_decoder_destroy", "vavae_decoder_load_weight", "vavae_decoder_finalize",
+    "vavae_decoder_decode", "vavae_decoder_launch_count", "vavae_decoder_device_bytes",
 ]
 
 
@@ -36,6 +38,13 @@ class VavaeConfig(ctypes.Structure):
 
 
 _lib = None
+
+
+class VavaeDecoderConfig(ctypes.Structure):
+    _fields_ = [("abi_version", ctypes.c_int32), ("z_channels", ctypes.c_int32), ("ch", ctypes.c_int32),
+                ("num_levels", ctypes.c_int32), ("ch_mult", ctypes.c_int32 * 8), ("num_res_blocks", ctypes.c_int32),
+                ("num_attn_res", ctypes.c_int32), ("attn_res", ctypes.c_int32 * 4), ("resolution", ctypes.c_int32),
+                ("out_ch", ctypes.c_int32), ("precision", ctypes.c_int32), ("max_batch", ctypes.c_int32)]
 
 
 def load_library() -> ctypes.CDLL:
@@ -77,6 +86,16 @@ def load_library() -> ctypes.CDLL:
     lib.vavae_profile_begin.argtypes = [c_void, ctypes.c_char_p]
     lib.vavae_profile_end.argtypes = [c_void, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64),
                                       ctypes.POINTER(ctypes.c_double)]
+    lib.vavae_decoder_create.argtypes = [ctypes.POINTER(VavaeDecoderConfig), c_int, ctypes.POINTER(c_void)]
+    lib.vavae_decoder_destroy.argtypes = [c_void]
+    lib.vavae_decoder_load_weight.argtypes = [c_void, ctypes.c_char_p, c_void, ctypes.POINTER(ctypes.c_int64), c_int,
+                                              c_int]
+    lib.vavae_decoder_finalize.argtypes = [c_void]
+    lib.vavae_decoder_decode.argtypes = [c_void, c_void, c_int, c_void, c_void, c_void]
+    lib.vavae_decoder_launch_count.argtypes = [c_void]
+    lib.vavae_decoder_launch_count.restype = ctypes.c_uint64
+    lib.vavae_decoder_device_bytes.argtypes = [c_void]
+    lib.vavae_decoder_device_bytes.restype = ctypes.c_uint64
     if "VAVAE_GEMM_2CTA" in os.environ:      # 0 = never, 1 = main-loop-bound GEMMs only, 2 = wherever possible (default)
         lib.vavae_set_gemm_two_cta(int(os.environ["VAVAE_GEMM_2CTA"]))
     if lib.vavae_abi_version() != ABI_VERSION:
