@@ -81,10 +81,23 @@ struct vavae_decoder {
 namespace {
 
 constexpr int GN_GROUPS = 32;          // autoencoder.py:15-18
-constexpr int GN_SLAB = 1024;          // pixels per partial-sum block
+constexpr int GN_SLAB = 512;           // pixels per partial-sum block
 inline int pad64(int c) { return (c + 63) / 64 * 64; }
 
 // ------------------------------------------------------------------------------------------------ kernels
+// eight consecutive operand channels in one store (16 bytes of bf16, or two float4 in the fp32 validation mode)
+__device__ __forceinline__ void store8(bf16* o, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+  pk.z = *reinterpret_cast<uint32_t*>(&c); pk.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(o) = pk;
+}
+__device__ __forceinline__ void store8(float* o, const float* v) {
+  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
 // z (n, zc, r, r) NCHW fp32 -> post_quant_conv (1x1, autoencoder.py:469,491) -> NHWC operand with padded channels
 template <typename OutT>
 __global__ void k_post_quant(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
@@ -114,11 +127,17 @@ __global__ void __launch_bounds__(256) k_gn_partial(const float* __restrict__ x,
   const int p0 = slab * GN_SLAB, p1 = min(hw, p0 + GN_SLAB);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   const float4* base = reinterpret_cast<const float4*>(x + (size_t)img * hw * C);
-  for (int p = p0 + lane; p < p1; p += lanes) {
-    const float4 v = base[(size_t)p * c4n + c4];
+  auto acc = [&](const float4 v) {
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+  };
+  int p = p0 + lane;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {   // four independent 16-byte loads in flight, fixed accumulation order
+    const float4 v0 = base[(size_t)p * c4n + c4], v1 = base[(size_t)(p + lanes) * c4n + c4];
+    const float4 v2 = base[(size_t)(p + 2 * lanes) * c4n + c4], v3 = base[(size_t)(p + 3 * lanes) * c4n + c4];
+    acc(v0); acc(v1); acc(v2); acc(v3);
   }
+  for (; p < p1; p += lanes) acc(base[(size_t)p * c4n + c4]);
   float* ss = sm;
   float* sq = sm + lanes * C;
   reinterpret_cast<float4*>(ss + lane * C)[c4] = s;
@@ -157,28 +176,30 @@ template <typename OutT>
 __global__ void k_gn_apply(const float* __restrict__ x, const float* __restrict__ stat, const float* __restrict__ gamma,
                            const float* __restrict__ beta, OutT* __restrict__ out, size_t npix, int hw, int C, int cpad,
                            int swish) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 4 output channels
-  const int c4p = cpad >> 2;
-  if (idx >= npix * c4p) return;
-  const int c = (int)(idx % c4p) * 4;
-  const size_t pix = idx / c4p;
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 output channels
+  const int c8p = cpad >> 3;
+  if (idx >= npix * c8p) return;
+  const int c = (int)(idx % c8p) * 8;
+  const size_t pix = idx / c8p;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < C) {
     const int img = (int)(pix / hw), cpg = C / GN_GROUPS;
-    const float4 xv = *reinterpret_cast<const float4*>(x + pix * C + c);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float4 x0 = *reinterpret_cast<const float4*>(x + pix * C + c), x1 = *reinterpret_cast<const float4*>(x + pix * C + c + 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
+    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const float gs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float2* st = reinterpret_cast<const float2*>(stat) + (size_t)img * GN_GROUPS;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (c + j) / cpg;
-      const float mean = stat[((size_t)img * GN_GROUPS + g) * 2], rstd = stat[((size_t)img * GN_GROUPS + g) * 2 + 1];
-      float y = (xs[j] - mean) * rstd * gamma[c + j] + beta[c + j];
+    for (int j = 0; j < 8; ++j) {
+      const float2 mr = st[(c + j) / cpg];   // (mean, rstd)
+      float y = (xs[j] - mr.x) * mr.y * gs[j] + bs[j];
       if (swish) y = y / (1.f + __expf(-y));
       v[j] = y;
     }
   }
-  OutT* o = out + pix * cpad + c;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) o[j] = (OutT)v[j];
+  store8(out + pix * cpad + c, v);
 }
 // fp32 [M, C] -> operand [M, cpad] (input of the 1x1 skip convolution)
 template <typename OutT>
@@ -192,15 +213,23 @@ __global__ void k_cvt_pad(const float* __restrict__ x, OutT* __restrict__ out, s
 // nearest-neighbour x2 upsampling (autoencoder.py:31) straight into the operand of the following 3x3 convolution
 template <typename OutT>
 __global__ void k_upsample2x(const float* __restrict__ x, OutT* __restrict__ out, int n, int H, int W, int C, int cpad) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)n * 4 * H * W * cpad;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 channels of an output pixel
+  const int c8p = cpad >> 3;
+  const size_t total = (size_t)n * 4 * H * W * c8p;
   if (idx >= total) return;
-  const int c = (int)(idx % cpad);
-  size_t pix = idx / cpad;
+  const int c = (int)(idx % c8p) * 8;
+  size_t pix = idx / c8p;
+  const size_t opix = pix;
   const int ox = (int)(pix % (2 * W));
   pix /= 2 * W;
   const int oy = (int)(pix % (2 * H)), img = (int)(pix / (2 * H));
-  out[idx] = (OutT)(c < C ? x[(((size_t)img * H + (oy >> 1)) * W + (ox >> 1)) * C + c] : 0.f);
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    const float* src = x + (((size_t)img * H + (oy >> 1)) * W + (ox >> 1)) * C + c;
+    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  store8(out + opix * cpad + c, v);
 }
 // fp32 validation mode: direct convolution, one thread per output element
 __global__ void k_conv_f32(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
@@ -290,7 +319,7 @@ struct Dec {
     const size_t npix = (size_t)n * hw;
     const float* g = d->W(name + ".weight").d;
     const float* b = d->W(name + ".bias").d;
-    launch1d(npix * (cpad / 4), s, [&](dim3 gr, dim3 bl, cudaStream_t st) {
+    launch1d(npix * (cpad / 8), s, [&](dim3 gr, dim3 bl, cudaStream_t st) {
       if (d->fp32) k_gn_apply<float><<<gr, bl, 0, st>>>(x, d->gn_stat, g, b, (float*)d->A, npix, hw, C, cpad, swish);
       else k_gn_apply<bf16><<<gr, bl, 0, st>>>(x, d->gn_stat, g, b, (bf16*)d->A, npix, hw, C, cpad, swish);
     });
@@ -547,7 +576,7 @@ void decode_chunk(vavae_decoder* d, const float* z, int n, float* out_nchw, uint
     }
     if (lvl != 0) {
       const int cpad = pad64(block_in);
-      launch1d((size_t)n * 4 * curr * curr * cpad, s, [&](dim3 gr, dim3 bl, cudaStream_t st) {
+      launch1d((size_t)n * 4 * curr * curr * (cpad / 8), s, [&](dim3 gr, dim3 bl, cudaStream_t st) {
         if (d->fp32) k_upsample2x<float><<<gr, bl, 0, st>>>(x, (float*)d->A, n, curr, curr, block_in, cpad);
         else k_upsample2x<bf16><<<gr, bl, 0, st>>>(x, (bf16*)d->A, n, curr, curr, block_in, cpad);
       });

@@ -163,7 +163,7 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 
 template <int EPI>
 __device__ __forceinline__ bool epi_fast_supported(const TcGemmArgs& a) {
-  if (EPI == TC_EPI_GATED_RESIDUAL || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_EMBED) return true;
+  if (EPI == TC_EPI_GATED_RESIDUAL || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_EMBED || EPI == TC_EPI_BIAS_F32) return true;
   if (EPI == TC_EPI_QKV) return a.qn_w == nullptr && a.kn_w == nullptr;
   return false;
 }
@@ -176,7 +176,8 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   constexpr int CW = 32, LPR = 8, RPP = 4, SST = (CW + 4) * 4;  // staging row stride in bytes
   const int prow = lane >> 3, pcc = (lane & 7) * 4;
   const int wrow0 = m0 + q * 32;
-  const int wb = wrow0 / a.T, wt0 = wrow0 - wb * a.T;
+  const int Tdiv = a.T > 0 ? a.T : 1;   // plain bias epilogues do not group rows into samples (T may be 0)
+  const int wb = wrow0 / Tdiv, wt0 = wrow0 - wb * Tdiv;
   const int n_chunks = BN / CW;
   const uint32_t st_w = st_s + (uint32_t)lane * SST;            // thread == row staging write base
   const uint32_t st_r = st_s + (uint32_t)prow * SST + pcc * 4;  // row-pass read base (+ ps * RPP * SST)
@@ -227,7 +228,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   prefetch(half);
   // consumer epilogues: the per-sample shift.W^T+bias vector lives in the big `mod` matrix (DRAM latency): request
   // the vectors of all (<= 4) chunks this warp will process before waiting for the accumulator
-  constexpr bool kBiasAhead = EPI == TC_EPI_SWIGLU || EPI == TC_EPI_EMBED;  // (QKV: register budget, stays one-ahead)
+  constexpr bool kBiasAhead = EPI == TC_EPI_SWIGLU || EPI == TC_EPI_EMBED || EPI == TC_EPI_BIAS_F32;  // (QKV: register budget, stays one-ahead)
   float4 bball[4];
   if (kBiasAhead) {
 #pragma unroll
@@ -317,6 +318,23 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         float4 v = lds128(st_r + ps * RPP * SST);
         v.x += bb.x + p4[ps].x; v.y += bb.y + p4[ps].y; v.z += bb.z + p4[ps].z; v.w += bb.w + p4[ps].w;
         *reinterpret_cast<float4*>(xo + (size_t)ps * RPP * a.ldo) = v;
+      }
+    } else if (EPI == TC_EPI_BIAS_F32) {
+      // acc + bias (+ fp32 residual, may alias the output): adaLN rows, decoder convolutions with their skip connection
+      const size_t off = (size_t)(wrow0 + prow) * a.ldo + n0 + c0 + pcc;
+      float* xo = reinterpret_cast<float*>(a.out) + off;
+      const size_t opass = (size_t)RPP * a.ldo;
+      float4 r4[LPR];
+      if (a.res) {
+#pragma unroll
+        for (int ps = 0; ps < LPR; ++ps) r4[ps] = *reinterpret_cast<const float4*>(a.res + off + ps * opass);
+      }
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) {
+        float4 v = lds128(st_r + ps * RPP * SST);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+        if (a.res) { v.x += r4[ps].x; v.y += r4[ps].y; v.z += r4[ps].z; v.w += r4[ps].w; }
+        *reinterpret_cast<float4*>(xo + ps * opass) = v;
       }
     } else if (EPI == TC_EPI_SWIGLU) {
       bf16* ho = reinterpret_cast<bf16*>(a.out) + (size_t)(wrow0 + prow) * a.ldo + ((n0 + c0 + pcc) >> 1);
@@ -660,7 +678,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     constexpr int RPP = 32 / LPR;  // rows per pass
     const int prow = lane / LPR;   // row (within a pass) and column group this lane owns in the row-wise pass
     const int pcc = (lane % LPR) * 4;
-    const bool rows_one_sample = (a.T % 32) == 0;  // the warp's 32 rows are consecutive tokens of one sample
+    // the warp's 32 rows are consecutive tokens of one sample (plain bias epilogues have no per-sample operands)
+    const bool rows_one_sample = EPI == TC_EPI_BIAS_F32 ? true : (a.T > 0 && (a.T % 32) == 0);
     const bool fast_ok = rows_one_sample && (BN % 32 == 0) && epi_fast_supported<EPI>(a) &&
                          (EPI != TC_EPI_QKV || ((a.H * a.hd) % 32 == 0 && a.hd % 4 == 0));
     int as = 0;
