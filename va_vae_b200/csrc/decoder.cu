@@ -174,17 +174,20 @@ __global__ void k_gn_final(const float* __restrict__ part, float* __restrict__ s
 // convolution's operand (channels padded with zeros up to cpad)
 template <typename OutT>
 __global__ void k_gn_apply(const float* __restrict__ x, const float* __restrict__ stat, const float* __restrict__ gamma,
-                           const float* __restrict__ beta, OutT* __restrict__ out, size_t npix, int hw, int C, int cpad,
-                           int swish) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per 8 output channels
-  const int c8p = cpad >> 3;
-  if (idx >= npix * c8p) return;
-  const int c = (int)(idx % c8p) * 8;
-  const size_t pix = idx / c8p;
+                           const float* __restrict__ beta, OutT* __restrict__ out, uint32_t npix, uint32_t hw, int C, int cpad,
+                           int cpg_shift, int swish) {
+  // one thread per 8 output channels; 32-bit index arithmetic (npix * cpad / 8 < 2^32 is checked by the launcher) and a
+  // shift for the channel -> group map (channels per group is a power of two)
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c8p = (uint32_t)cpad >> 3;
+  const uint32_t pix = idx / c8p;
+  if (pix >= npix) return;
+  const int c = (int)(idx - pix * c8p) * 8;
   float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    const int img = (int)(pix / hw), cpg = C / GN_GROUPS;
-    const float4 x0 = *reinterpret_cast<const float4*>(x + pix * C + c), x1 = *reinterpret_cast<const float4*>(x + pix * C + c + 4);
+    const uint32_t img = pix / hw;
+    const float* xp = x + (size_t)pix * C + c;
+    const float4 x0 = *reinterpret_cast<const float4*>(xp), x1 = *reinterpret_cast<const float4*>(xp + 4);
     const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(beta + c), b1 = *reinterpret_cast<const float4*>(beta + c + 4);
     const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -193,13 +196,13 @@ __global__ void k_gn_apply(const float* __restrict__ x, const float* __restrict_
     const float2* st = reinterpret_cast<const float2*>(stat) + (size_t)img * GN_GROUPS;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float2 mr = st[(c + j) / cpg];   // (mean, rstd)
+      const float2 mr = st[(c + j) >> cpg_shift];   // (mean, rstd)
       float y = (xs[j] - mr.x) * mr.y * gs[j] + bs[j];
       if (swish) y = y / (1.f + __expf(-y));
       v[j] = y;
     }
   }
-  store8(out + pix * cpad + c, v);
+  store8(out + (size_t)pix * cpad + c, v);
 }
 // fp32 [M, C] -> operand [M, cpad] (input of the 1x1 skip convolution)
 template <typename OutT>
@@ -319,9 +322,12 @@ struct Dec {
     const size_t npix = (size_t)n * hw;
     const float* g = d->W(name + ".weight").d;
     const float* b = d->W(name + ".bias").d;
+    int cpg_shift = 0;
+    while ((1 << cpg_shift) < C / GN_GROUPS) ++cpg_shift;
+    VV_CHECK((1 << cpg_shift) == C / GN_GROUPS && npix * (size_t)(cpad / 8) < 0xFFFFFFFFull, "decoder: GroupNorm index range");
     launch1d(npix * (cpad / 8), s, [&](dim3 gr, dim3 bl, cudaStream_t st) {
-      if (d->fp32) k_gn_apply<float><<<gr, bl, 0, st>>>(x, d->gn_stat, g, b, (float*)d->A, npix, hw, C, cpad, swish);
-      else k_gn_apply<bf16><<<gr, bl, 0, st>>>(x, d->gn_stat, g, b, (bf16*)d->A, npix, hw, C, cpad, swish);
+      if (d->fp32) k_gn_apply<float><<<gr, bl, 0, st>>>(x, d->gn_stat, g, b, (float*)d->A, (uint32_t)npix, (uint32_t)hw, C, cpad, cpg_shift, swish);
+      else k_gn_apply<bf16><<<gr, bl, 0, st>>>(x, d->gn_stat, g, b, (bf16*)d->A, (uint32_t)npix, (uint32_t)hw, C, cpad, cpg_shift, swish);
     });
   }
   void cvt_pad(const float* x, int hw, int C) {
