@@ -466,9 +466,6 @@ void pack_conv(vavae_decoder* d, const std::string& name, const std::vector<std:
   d->convs[name] = c;
 }
 
-struct Plan {
-  int block_in, z_res;
-};
 inline bool has_attn(const vavae_decoder_config_t& c, int res) {
   for (int i = 0; i < c.num_attn_res; ++i)
     if (c.attn_res[i] == res) return true;
