@@ -58,6 +58,7 @@ struct vavae_decoder {
   float* Sc = nullptr;                               // attention scores [T, T] fp32 (one image at a time)
   float* gn_part = nullptr;                          // [n][slabs][32][2]
   float* gn_stat = nullptr;                          // [n][32][2] (mean, rstd)
+  float* gn_wide = nullptr;                          // [n][hw/32][32][2] partial sums emitted by GEMM epilogues
   int max_slabs = 0;
 
   template <typename Tp>
@@ -169,6 +170,29 @@ __global__ void k_gn_final(const float* __restrict__ part, float* __restrict__ s
   const double var = fmax(b / count - mean * mean, 0.0);
   stat[((size_t)img * GN_GROUPS + g) * 2] = (float)mean;
   stat[((size_t)img * GN_GROUPS + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-6));
+}
+// stage 2 for statistics emitted by the producing GEMM's epilogue (32-row slabs, many more of them): 8 threads per
+// group walk interleaved slabs in double precision and are combined in a fixed order
+__global__ void __launch_bounds__(256) k_gn_final_wide(const float* __restrict__ part, float* __restrict__ stat, int slabs,
+                                                       double count) {
+  __shared__ double sa[256], sb[256];
+  const int img = blockIdx.x, g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  double a = 0.0, b = 0.0;
+  for (int s = sub; s < slabs; s += 8) {
+    const float2 v = reinterpret_cast<const float2*>(part)[((size_t)img * slabs + s) * GN_GROUPS + g];
+    a += (double)v.x;
+    b += (double)v.y;
+  }
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  if (sub == 0) {
+    for (int i = 1; i < 8; ++i) { a += sa[threadIdx.x + i]; b += sb[threadIdx.x + i]; }
+    const double mean = a / count;
+    const double var = fmax(b / count - mean * mean, 0.0);
+    stat[((size_t)img * GN_GROUPS + g) * 2] = (float)mean;
+    stat[((size_t)img * GN_GROUPS + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-6));
+  }
 }
 // stage 3: y = (x - mean) * rstd * gamma + beta, optional swish (autoencoder.py:10-12), written as the next
 // convolution's operand (channels padded with zeros up to cpad)
@@ -310,14 +334,29 @@ struct Dec {
   vavae_decoder* d;
   cudaStream_t s;
   int n;   // images in this chunk
+  const float* stats_of = nullptr;   // tensor whose GroupNorm partial sums the last GEMM epilogue left in d->gn_wide
+
+  // can the GEMM writing [n*hw, C] fp32 emit the statistics of its output?  (tensor-core path, interior tiles only)
+  bool can_emit(int hw, int C) const {
+    const int cpg = C / GN_GROUPS;
+    return !d->fp32 && d->gn_wide && cpg >= 4 && cpg <= 32 && (cpg & (cpg - 1)) == 0 && hw % 32 == 0 &&
+           ((size_t)n * hw) % 128 == 0 && C % 128 == 0;
+  }
 
   void group_norm(const float* x, const std::string& name, int hw, int C, bool swish) {
-    const int slabs = cdiv(hw, GN_SLAB), c4n = C / 4, lanes = 256 / c4n;
-    VV_CHECK(slabs <= d->max_slabs, "decoder: GroupNorm workspace too small");
-    k_gn_partial<<<dim3(slabs, n), 256, (size_t)2 * lanes * C * sizeof(float), s>>>(x, d->gn_part, hw, C, slabs);
-    VV_LAUNCH_CHECK();
-    k_gn_final<<<n, GN_GROUPS, 0, s>>>(d->gn_part, d->gn_stat, slabs, (double)hw * (C / GN_GROUPS));
-    VV_LAUNCH_CHECK();
+    if (stats_of == x) {
+      // the producing GEMM already left per-slab sums: finish them (no pass over the activations)
+      k_gn_final_wide<<<n, 256, 0, s>>>(d->gn_wide, d->gn_stat, hw / 32, (double)hw * (C / GN_GROUPS));
+      VV_LAUNCH_CHECK();
+    } else {
+      const int slabs = cdiv(hw, GN_SLAB), c4n = C / 4, lanes = 256 / c4n;
+      VV_CHECK(slabs <= d->max_slabs, "decoder: GroupNorm workspace too small");
+      k_gn_partial<<<dim3(slabs, n), 256, (size_t)2 * lanes * C * sizeof(float), s>>>(x, d->gn_part, hw, C, slabs);
+      VV_LAUNCH_CHECK();
+      k_gn_final<<<n, GN_GROUPS, 0, s>>>(d->gn_part, d->gn_stat, slabs, (double)hw * (C / GN_GROUPS));
+      VV_LAUNCH_CHECK();
+    }
+    stats_of = nullptr;
     const int cpad = pad64(C);
     const size_t npix = (size_t)n * hw;
     const float* g = d->W(name + ".weight").d;
@@ -339,7 +378,7 @@ struct Dec {
     });
   }
   // out[n*H*W, ldo] = conv(A operand) + bias (+ res); 3x3 pad 1 or 1x1
-  void conv(const std::string& name, int H, int W, float* out, const float* res) {
+  void conv(const std::string& name, int H, int W, float* out, const float* res, bool emit_stats = false) {
     auto it = d->convs.find(name);
     VV_CHECK(it != d->convs.end(), "decoder: convolution '" + name + "' was not packed");
     const ConvPack& c = it->second;
@@ -360,11 +399,18 @@ struct Dec {
     g.T = 32;   // unused by this epilogue (rows are not grouped into samples)
     g.conv_taps = c.taps; g.conv_H = H; g.conv_W = W;
     if (c.taps == 1) g.conv_taps = 0;   // 1x1: rows of the NHWC operand are the GEMM rows already
+    if (out == stats_of) stats_of = nullptr;
+    if (emit_stats && can_emit(H * W, c.cout) && c.cout == c.cout_pad) {
+      int sh = 0;
+      while ((1 << sh) < c.cout / GN_GROUPS) ++sh;
+      g.gn_part = d->gn_wide; g.gn_hw = H * W; g.gn_cpg_shift = sh;
+      stats_of = out;
+    }
     launch_gemm_tc(g, s);
   }
   // C[M, N] (+bias) = A[M, K] B[N, K]^T with operand-typed inputs; out_f32 selects the fp32 or the operand-typed output
   void gemm_nt(const void* A_, int lda, const void* B_, int ldb, const float* bias, void* C_, int ldc, int M, int N, int K,
-               bool out_f32, const float* res = nullptr) {
+               bool out_f32, const float* res = nullptr, int emit_hw = 0) {
     if (d->fp32) {
       launch1d((size_t)M * N, s, [&](dim3 gr, dim3 bl, cudaStream_t st) {
         k_gemm_nt_f32<<<gr, bl, 0, st>>>((const float*)A_, lda, (const float*)B_, ldb, bias, res, (float*)C_, ldc, M, N, K);
@@ -377,6 +423,13 @@ struct Dec {
     g.M = M; g.N = N; g.K = K; g.bias = bias; g.out = C_; g.ldo = ldc; g.T = 32;
     g.epi = out_f32 ? TC_EPI_BIAS_F32 : TC_EPI_BIAS_BF16;
     g.res = res;
+    if (C_ == (const void*)stats_of) stats_of = nullptr;
+    if (emit_hw > 0 && out_f32 && ldc == N && can_emit(emit_hw, N)) {
+      int sh = 0;
+      while ((1 << sh) < N / GN_GROUPS) ++sh;
+      g.gn_part = d->gn_wide; g.gn_hw = emit_hw; g.gn_cpg_shift = sh;
+      stats_of = (const float*)C_;
+    }
     launch_gemm_tc(g, s);
   }
 
@@ -390,9 +443,9 @@ struct Dec {
       skip = spare;
     }
     group_norm(x, name + ".norm1", hw, cin, true);
-    conv(name + ".conv1", H, W, d->Hc, nullptr);
+    conv(name + ".conv1", H, W, d->Hc, nullptr, true);
     group_norm(d->Hc, name + ".norm2", hw, cout, true);
-    conv(name + ".conv2", H, W, skip, skip);   // skip + conv2(...), in place
+    conv(name + ".conv2", H, W, skip, skip, true);   // skip + conv2(...), in place
     return skip;
   }
   // autoencoder.py:135-160
@@ -421,7 +474,7 @@ struct Dec {
     // proj_out (1x1) + residual, in place on x
     const ConvPack& po = d->convs.at(name + ".proj_out");
     const void* wp = d->fp32 ? (const void*)po.w_f : (const void*)po.w_h;
-    gemm_nt(d->O, C, wp, cp, po.b, x, C, n * T, C, C, true, x);
+    gemm_nt(d->O, C, wp, cp, po.b, x, C, n * T, C, C, true, x, T);
   }
 };
 
@@ -543,6 +596,7 @@ void finalize(vavae_decoder* d) {
   }
   d->gn_part = d->alloc<float>(nb * d->max_slabs * GN_GROUPS * 2);
   d->gn_stat = d->alloc<float>(nb * GN_GROUPS * 2);
+  if (!d->fp32) d->gn_wide = d->alloc<float>(nb * (size_t)(c.resolution * c.resolution / 32 + 1) * GN_GROUPS * 2);
   d->finalized = true;
 }
 
@@ -561,7 +615,7 @@ void decode_chunk(vavae_decoder* d, const float* z, int n, float* out_nchw, uint
   });
   float* x = d->X;
   float* spare = d->Y;
-  k.conv("decoder.conv_in", curr, curr, x, nullptr);
+  k.conv("decoder.conv_in", curr, curr, x, nullptr, true);
   auto run_res = [&](const std::string& name, int cin, int cout) {
     float* r = k.resnet(name, x, spare, curr, curr, cin, cout);
     if (r != x) std::swap(x, spare);
@@ -584,7 +638,7 @@ void decode_chunk(vavae_decoder* d, const float* z, int n, float* out_nchw, uint
         else k_upsample2x<bf16><<<gr, bl, 0, st>>>(x, (bf16*)d->A, n, curr, curr, block_in, cpad);
       });
       curr *= 2;
-      k.conv("decoder.up." + std::to_string(lvl) + ".upsample.conv", curr, curr, spare, nullptr);
+      k.conv("decoder.up." + std::to_string(lvl) + ".upsample.conv", curr, curr, spare, nullptr, true);
       std::swap(x, spare);
     }
   }

@@ -329,12 +329,32 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
 #pragma unroll
         for (int ps = 0; ps < LPR; ++ps) r4[ps] = *reinterpret_cast<const float4*>(a.res + off + ps * opass);
       }
+      float4 gs = make_float4(0.f, 0.f, 0.f, 0.f), gq = gs;   // per-channel sum / sum of squares over this lane's 8 rows
 #pragma unroll
       for (int ps = 0; ps < LPR; ++ps) {
         float4 v = lds128(st_r + ps * RPP * SST);
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
         if (a.res) { v.x += r4[ps].x; v.y += r4[ps].y; v.z += r4[ps].z; v.w += r4[ps].w; }
         *reinterpret_cast<float4*>(xo + ps * opass) = v;
+        gs.x += v.x; gs.y += v.y; gs.z += v.z; gs.w += v.w;
+        gq.x += v.x * v.x; gq.y += v.y * v.y; gq.z += v.z * v.z; gq.w += v.w * v.w;
+      }
+      if (a.gn_part) {
+        // GroupNorm statistics of the tensor just written, for the normalisation that follows: this warp's 32 rows x
+        // this chunk's 32 columns -> one (sum, sum of squares) per group, fixed reduction order (no atomics)
+        float sg = (gs.x + gs.y) + (gs.z + gs.w), qg = (gq.x + gq.y) + (gq.z + gq.w);   // 4 channels of one group
+        sg += __shfl_xor_sync(0xffffffffu, sg, 8);  qg += __shfl_xor_sync(0xffffffffu, qg, 8);    // rows: lane bits 3, 4
+        sg += __shfl_xor_sync(0xffffffffu, sg, 16); qg += __shfl_xor_sync(0xffffffffu, qg, 16);
+        for (int o = 1; o < (1 << (a.gn_cpg_shift - 2)); o <<= 1) {   // groups wider than 4 channels: neighbouring lanes
+          sg += __shfl_xor_sync(0xffffffffu, sg, o);
+          qg += __shfl_xor_sync(0xffffffffu, qg, o);
+        }
+        if (prow == 0 && ((lane & 7) & ((1 << (a.gn_cpg_shift - 2)) - 1)) == 0) {
+          const int img = wrow0 / a.gn_hw, slab = (wrow0 - img * a.gn_hw) >> 5, slabs = a.gn_hw >> 5;
+          const int g = (n0 + c0 + pcc) >> a.gn_cpg_shift;
+          float2* o2 = reinterpret_cast<float2*>(a.gn_part) + ((size_t)img * slabs + slab) * 32 + g;
+          *o2 = make_float2(sg, qg);
+        }
       }
     } else if (EPI == TC_EPI_SWIGLU) {
       bf16* ho = reinterpret_cast<bf16*>(a.out) + (size_t)(wrow0 + prow) * a.ldo + ((n0 + c0 + pcc) >> 1);
@@ -1184,6 +1204,12 @@ void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
     VV_CHECK(a.conv_W >= 128 ? a.conv_W % 128 == 0 : 128 % a.conv_W == 0, "gemm_tc: conv width must divide or be a multiple of 128");
   }
   VV_CHECK(a.res == nullptr || a.epi == TC_EPI_BIAS_F32, "gemm_tc: residual input only with the fp32 bias epilogue");
+  if (a.gn_part) {
+    const int bn = gemm_tc_pick_bn(a);
+    VV_CHECK(a.epi == TC_EPI_BIAS_F32 && a.M % TC_BM == 0 && a.N % bn == 0 && bn % 32 == 0 && a.gn_hw % 32 == 0 &&
+                 a.M % a.gn_hw == 0 && a.gn_cpg_shift >= 2 && a.gn_cpg_shift <= 5,
+             "gemm_tc: GroupNorm statistics need interior tiles, 32-row slabs inside one image and 4..32 channels per group");
+  }
   const int BN = gemm_tc_pick_bn(a);
   int cw = (BN % 32 == 0) ? 32 : 16;
   if (a.epi == TC_EPI_QKV && (a.H * a.hd) % 32 != 0) cw = 16;

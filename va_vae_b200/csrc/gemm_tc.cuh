@@ -62,6 +62,12 @@ struct TcGemmArgs {
   int conv_taps, conv_H, conv_W;
   // TC_EPI_BIAS_F32 only: optional fp32 residual [M, ldo] added to acc + bias (may alias `out`)
   const float* res;
+  // TC_EPI_BIAS_F32 only, optional: GroupNorm partial statistics of the OUTPUT for the normalisation that follows -
+  // per (image, 32-row slab, group) sum and sum of squares: gn_part[((img * (gn_hw/32) + slab) * 32 + group) * 2 + {0,1}]
+  // with group = column >> gn_cpg_shift (channels per group a power of two >= 4).  Requires every tile to be interior
+  // (M % 128 == 0, N % tile width == 0): launch_gemm_tc checks it.
+  float* gn_part;
+  int gn_hw, gn_cpg_shift;
 };
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
