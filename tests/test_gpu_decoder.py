@@ -59,6 +59,21 @@ def test_production_geometry_one_image_vs_oracle():
     assert diff.mean() <= 1.5
 
 
+def test_resolution_512_rows_wider_than_one_tile():
+    """32x32 latent -> 512x512 (VA_VAE(img_size=512)): image rows span several 128-pixel TMA boxes, attention only in the
+    middle block (32x32 = 1024 positions).  Narrow channels keep the CPU oracle fast."""
+    cfg = D.DecoderConfig(z_channels=32, ch=32, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=1, attn_resolutions=(16,),
+                          resolution=512)
+    sd = D.init_state_dict(cfg, seed=21)
+    z = torch.randn(1, 32, 32, 32, generator=torch.Generator().manual_seed(22))
+    ref = D.decode(cfg, sd, z)
+    for precision, tol in (("fp32", 1e-5), ("bf16", 2e-2)):
+        m = build(cfg, sd, precision)
+        out = m.decode(z.cuda())
+        assert out.shape == (1, 3, 512, 512)
+        assert rel_l2(out, ref) < tol, precision
+
+
 def test_batch_chunking_and_determinism():
     cfg = D.DecoderConfig(z_channels=32, ch=32, ch_mult=(1, 2, 4), num_res_blocks=2, attn_resolutions=(16,), resolution=64)
     sd = D.init_state_dict(cfg, seed=12)
