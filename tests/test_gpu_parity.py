@@ -311,3 +311,22 @@ def test_results_do_not_depend_on_sharding_or_batch_size():
             lo, hi = shard_range(n, r, world)
             parts.append(sample(z[lo:hi], y[lo:hi]))
         assert torch.equal(torch.cat(parts, 0), whole), f"world {world}: sharded result differs from the single-GPU result"
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("method", ["Euler", "Heun"])
+def test_sde_sampler_native_forward_vs_oracle_forward(precision, tol, method):
+    """Sampler.sample_sde (transport.py:336-396): the same host loop and noise stream driven once by the native
+    forward_with_cfg on the GPU and once by the CPU oracle's forward_with_cfg."""
+    import va_vae_b200 as V
+    cfg, sd, z, y = _oracle_case("LightningDiT-S/1", 2, num_classes=31)
+    m = _engine_model("LightningDiT-S/1", cfg, sd, precision)
+    zz, yy = torch.cat([z, z]), torch.cat([y, torch.full_like(y, 31)])
+    mk = lambda: V.Sampler(V.create_transport("Linear", "velocity", None, None, None)).sample_sde(
+        sampling_method=method, diffusion_form="sigma", diffusion_norm=1.0, last_step="Mean", last_step_size=0.04, num_steps=5)
+    torch.manual_seed(77)
+    ref = mk()(zz, lambda x, t, **kw: O.forward_with_cfg(cfg, sd, x, t, kw["y"], kw["cfg_scale"]), y=yy, cfg_scale=4.0)
+    torch.manual_seed(77)
+    out = mk()(zz.cuda(), m.forward_with_cfg, y=yy.cuda(), cfg_scale=4.0)
+    assert len(out) == len(ref) == 5
+    assert rel_l2(out[-1], ref[-1]) < tol

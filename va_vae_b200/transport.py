@@ -1,9 +1,9 @@
-"""Mirror of the reference's `transport` sampling API (create_transport / Sampler.sample_ode), ODE side only.
+"""Mirror of the reference's `transport` sampling API (create_transport / Sampler.sample_ode / Sampler.sample_sde).
 
 Reference: /root/reference/LightningDiT/transport/__init__.py:3-72 (create_transport),
 transport/transport.py:40-111,218-250,270-283,398-443 (Transport.check_interval / get_drift, Sampler.sample_ode),
-transport/integrators.py:77-126 (class ode).  Training losses, SDE sampling and likelihoods are out of
-scope for this engine.
+transport/integrators.py:77-126 (class ode), plus Sampler.sample_sde (transport.py:336-396, integrators.py:8-75) for the
+linear path.  Training losses and likelihoods are out of scope for this engine.
 
 `sample_fn = Sampler(transport).sample_ode(...)` returns a bound `ode.sample` exactly like the reference; when
 `sample_fn(x, model.forward_with_cfg, **kw)` (or `model.forward`) is called with a bound method of the B200
@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import enum
 
+import numpy as np
 import torch as th
 
 
@@ -281,8 +282,107 @@ class Sampler:
                    timestep_shift=timestep_shift, keep_trajectory=keep_trajectory, native_ok=native_ok)
         return _ode.sample
 
-    def sample_sde(self, *a, **k):
-        raise NotImplementedError("SDE sampling is out of scope for the B200 ODE sampling engine")
+    def sample_sde(self, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean",
+                   last_step_size=0.04, num_steps=250):
+        """transport/transport.py:336-396 with the integrator of transport/integrators.py:8-75, for the linear path with
+        a velocity model (the only combination the reference's configs create).  Same arguments, same time grid, same
+        noise stream (``th.randn(x.size()).to(x)`` drawn from the global CPU generator once per step, as the reference
+        does), same list of ``num_steps`` states as return value.  The reference evaluates the model twice per drift
+        (once for the velocity, once for the score, transport.py:306-308); both are derived here from ONE evaluation,
+        which is bit-identical for a deterministic model and halves the cost.  Every model evaluation is a native
+        forward when ``model`` is a bound method of the B200 module; the elementwise update runs in PyTorch."""
+        if self.transport.path_type != PathType.LINEAR or self.transport.model_type != ModelType.VELOCITY:
+            raise NotImplementedError("sample_sde covers path_type='Linear' with prediction='velocity'")
+        if sampling_method not in ("Euler", "Heun"):
+            raise NotImplementedError("Smapler type not implemented.")       # integrators.py:61 (sic)
+        if last_step not in (None, "Mean", "Tweedie", "Euler"):
+            raise NotImplementedError()
+        if last_step is None:
+            last_step_size = 0.0
+        t0, t1 = self.transport.check_interval(self.transport.train_eps, self.transport.sample_eps,
+                                               diffusion_form=diffusion_form, sde=True, eval=True, reverse=False,
+                                               last_step_size=last_step_size)
+        t_grid = th.linspace(t0, t1, num_steps)                               # integrators.py:24
+        dt = t_grid[1] - t_grid[0]
+
+        def expand(t, x):                                                     # path.py:5-13
+            return t.view(-1, *([1] * (x.dim() - 1)))
+
+        def diffusion_fn(x, t):                                               # path.py:45-68 on ICPlan (:23-43)
+            t = expand(t, x)
+            choices = {
+                "constant": lambda: diffusion_norm,
+                "SBDM": lambda: diffusion_norm * ((1 / t) * ((1 - t) ** 2) - (1 - t) * (-1)),
+                "sigma": lambda: diffusion_norm * (1 - t),
+                "linear": lambda: diffusion_norm * (1 - t),
+                "decreasing": lambda: 0.25 * (diffusion_norm * th.cos(np.pi * t) + 1) ** 2,
+                "inccreasing-decreasing": lambda: diffusion_norm * th.sin(np.pi * t) ** 2,
+            }
+            if diffusion_form not in choices:
+                raise NotImplementedError(f"Diffusion form {diffusion_form} not implemented")
+            return choices[diffusion_form]()
+
+        def score_from_velocity(v, x, t):                                     # path.py:70-84 with alpha = t, sigma = 1 - t
+            t = expand(t, x)
+            sigma_t = 1 - t
+            var = sigma_t ** 2 - (t / 1) * (-1) * sigma_t
+            return ((t / 1) * v - x) / var
+
+        def velocity(x, t, model, **kw):
+            out = model(x, t, **kw)
+            assert out.shape == x.shape, "Output shape from ODE solver must match input shape"
+            return out
+
+        def sde_drift(x, t, model, **kw):                                     # transport.py:306-308, one evaluation
+            v = velocity(x, t, model, **kw)
+            return v + diffusion_fn(x, t) * score_from_velocity(v, x, t)
+
+        def em_step(x, ti, model, **kw):                                      # integrators.py:30-38
+            w_cur = th.randn(x.size()).to(x)
+            t = th.ones(x.size(0)).to(x) * ti
+            dw = w_cur * th.sqrt(dt)
+            drift = sde_drift(x, t, model, **kw)
+            diffusion = diffusion_fn(x, t)
+            mean_x = x + drift * dt
+            return mean_x + th.sqrt(2 * diffusion) * dw
+
+        def heun_step(x, ti, model, **kw):                                    # integrators.py:40-49
+            w_cur = th.randn(x.size()).to(x)
+            dw = w_cur * th.sqrt(dt)
+            t_cur = th.ones(x.size(0)).to(x) * ti
+            diffusion = diffusion_fn(x, t_cur)
+            xhat = x + th.sqrt(2 * diffusion) * dw
+            k1 = sde_drift(xhat, t_cur, model, **kw)
+            xp = xhat + dt * k1
+            k2 = sde_drift(xp, t_cur + dt, model, **kw)
+            return xhat + 0.5 * dt * (k1 + k2)
+
+        step = em_step if sampling_method == "Euler" else heun_step
+
+        def last_step_fn(x, t, model, **kw):                                  # transport.py:313-334
+            if last_step is None:
+                return x
+            if last_step == "Mean":
+                return x + sde_drift(x, t, model, **kw) * last_step_size
+            if last_step == "Tweedie":
+                alpha, sigma = t[0], 1 - t[0]                                 # alpha(t)[0][0], sigma(t)[0][0]
+                v = velocity(x, t, model, **kw)
+                return x / alpha + (sigma ** 2) / alpha * score_from_velocity(v, x, t)
+            return x + velocity(x, t, model, **kw) * last_step_size           # "Euler"
+
+        def _sample(init, model, **model_kwargs):
+            x = init
+            xs = []
+            with th.no_grad():
+                for ti in t_grid[:-1]:                                        # integrators.py:69-73
+                    x = step(x, ti, model, **model_kwargs)
+                    xs.append(x)
+                ts = th.ones(init.size(0), device=init.device) * t1
+                xs.append(last_step_fn(xs[-1], ts, model, **model_kwargs))
+            assert len(xs) == num_steps, "Samples does not match the number of steps"
+            return xs
+
+        return _sample
 
     def sample_ode_likelihood(self, *a, **k):
         raise NotImplementedError("likelihood evaluation is out of scope for the B200 ODE sampling engine")
