@@ -423,6 +423,26 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         } else {
           // online softmax: rescale the running O (and running row sum in column hd) and add this block
+          if (OACC == 80) {
+            // head_dim 64 / 72: all 80 columns requested at once, one wait, TMEM released before the arithmetic
+            uint32_t o0[32], o1[32], o2[16];
+            ptx::tmem_ld_x32(trow + O_COL, o0);
+            ptx::tmem_ld_x32(trow + O_COL + 32, o1);
+            ptx::tmem_ld_x16(trow + O_COL + 64, o2);
+            tmem_ld_wait_dep32(o0);
+            tmem_ld_wait_dep32(o1);
+            tmem_ld_wait_dep16(o2);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&bars->o_empty);
+#pragma unroll
+            for (int j = 0; j < (OACC == 80 ? 32 : 0); ++j) {
+              oacc[j] = oacc[j] * alpha + __uint_as_float(o0[j]);
+              oacc[(OACC == 80 ? 32 : 0) + j] = oacc[(OACC == 80 ? 32 : 0) + j] * alpha + __uint_as_float(o1[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < (OACC == 80 ? 16 : 0); ++j)
+              oacc[(OACC == 80 ? 64 : 0) + j] = oacc[(OACC == 80 ? 64 : 0) + j] * alpha + __uint_as_float(o2[j]);
+          } else {
           for (int c0 = 0; c0 < ncol_o; c0 += 16) {
             uint32_t r[16];
             ptx::tmem_ld_x16(trow + O_COL + c0, r);
@@ -438,6 +458,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(&bars->o_empty);
+          }
           if (last) {
             float l = 0.f;
 #pragma unroll
