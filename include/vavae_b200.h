@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VAVAE_ABI_VERSION 1
+#define VAVAE_ABI_VERSION 2
 
 /* precision modes */
 #define VAVAE_PREC_BF16 0 /* tcgen05 bf16 tensor-core path, fp32 accumulate / residual / statistics */
@@ -93,15 +93,24 @@ int vavae_forward_with_cfg(vavae_engine_t* e, const float* x, const float* t, co
  * inference.py:205-211.  out_final receives the last grid point ([-1] of the reference trajectory).
  * out_trace: optional (NULL to skip) device buffer of (n_evals, batch, C, H, W) f32 receiving every
  * evaluation's velocity in call order (n_evals = n_points-1 for Euler, 2*(n_points-1) for Heun). */
+/* flags (bit set):
+ *   VAVAE_SAMPLE_SKIP_DISCARDED: with use_cfg=1 and cfg_interval=1, an evaluation at t < cfg_interval_start keeps only the
+ *   conditional output - the reference still computes the unconditional forward and throws it away
+ *   (models/lightningdit.py:436-439).  With this flag the engine runs the n conditional rows only for those
+ *   evaluations.  Rows [0, n) of out_final (the half every caller keeps, inference.py:216-218) are bit-identical to the
+ *   literal mode; rows [n, 2n) then follow the conditional velocity on every channel instead of the discarded
+ *   unconditional one, so leave the flag clear when the literal (2n, C, H, W) state of the reference is needed. */
+#define VAVAE_SAMPLE_SKIP_DISCARDED 1
 int vavae_sample_ode(vavae_engine_t* e, const float* z, const int64_t* y, const float* t_grid, int n_points,
                      int method, int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start,
-                     int cfg_channels, float* out_final, float* out_trace, int batch, void* stream);
+                     int cfg_channels, float* out_final, float* out_trace, int batch, int flags, void* stream);
 
 /* Same as vavae_sample_ode with HOST buffers for z, y and out_final (H2D / D2H copies inside the call;
  * synchronises the stream before returning).  This is the end-to-end entry bench.py times as `e2e`. */
 int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t* y_host, const float* t_grid,
                           int n_points, int method, int use_cfg, float cfg_scale, int cfg_interval,
-                          float cfg_interval_start, int cfg_channels, float* out_final_host, int batch, void* stream);
+                          float cfg_interval_start, int cfg_channels, float* out_final_host, int batch, int flags,
+                          void* stream);
 
 /* Replaces sample_fn built with sampling_method="dopri5" (the default of Sampler.sample_ode, transport/transport.py:401,
  * and what the fork's generation scripts use): adaptive Dormand-Prince 5(4) from t0 to t1 with torchdiffeq's step
@@ -113,8 +122,17 @@ int vavae_sample_dopri5(vavae_engine_t* e, const float* z, const int64_t* y, dou
                         int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start, int cfg_channels,
                         float* out_final, int batch, int64_t* stats, void* stream);
 
+/* nn.Embedding raises on a label outside the table (models/lightningdit.py:168); a kernel cannot.  The engine's label
+ * gathers clamp such an index to row 0 (never an out-of-bounds read) and raise a device flag; this call synchronises
+ * `stream`, returns non-zero ("index out of range in self") if the flag was raised since the last check, and clears it.
+ * The *_host entry points perform the same check before returning. */
+int vavae_device_status(vavae_engine_t* e, void* stream);
+
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 uint64_t vavae_launch_count(const vavae_engine_t* e);
+/* Model rows pushed through the layer stack since creation (= forwards actually executed; bench.py reports
+ * utilisation against this, so a skipped unconditional forward is never claimed as work). */
+uint64_t vavae_forward_rows(const vavae_engine_t* e);
 /* Bytes of device memory the engine owns (weights + workspace). */
 uint64_t vavae_device_bytes(const vavae_engine_t* e);
 const char* vavae_last_error(void);
@@ -139,6 +157,49 @@ int vavae_test_gemm_bf16(const void* A, const void* W, const float* bias, float*
  * (see DESIGN.md "attention layouts"). */
 int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void* out, int B, int H, int T, int hd,
                               void* stream);
+/* One launch of the production tcgen05 GEMM with one of its fused epilogues, on caller-provided device operands, so
+ * each epilogue can be checked against an fp32 reference of the same op (tests/test_gpu_epilogues.py):
+ *   VAVAE_EPI_QKV            attn.qkv: + bias, [qk RMSNorm], RoPE (models/pos_embed.py:38-42,135), q/k scattered head-major
+ *                            (B,H,T,hdp) and V stored transposed (B,H,hdv,T)   (models/lightningdit.py:66-76)
+ *   VAVAE_EPI_SWIGLU         mlp.w12: + bias, silu(x1) * x2 on row-interleaved weights (models/swiglu_ffn.py:31-36)
+ *   VAVAE_EPI_GATED_RESIDUAL attn.proj / mlp.w3: X += gate[b] * (acc + bias) (models/lightningdit.py:248-249), optionally
+ *                            emitting the next RMSNorm's un-normalised bf16 operand and per-row partial sums of squares
+ * Optional consumer-side fused RMSNorm (kinds QKV, SWIGLU): accumulator rows are scaled by
+ * rsqrt(sum(in_part[row, :in_nparts]) / in_dim + 1e-6) and sp[row / T, :] replaces the bias. */
+#define VAVAE_EPI_QKV 0
+#define VAVAE_EPI_SWIGLU 1
+#define VAVAE_EPI_GATED_RESIDUAL 2
+typedef struct vavae_epilogue_test {
+  int32_t kind;
+  int32_t M, N, K, T;       /* token rows, output columns, reduction length, tokens per sample (T % 32 == 0 for the fast path) */
+  const void* A;            /* bf16 [M, K] */
+  const void* W;            /* bf16 [N, K]; SWIGLU: rows interleaved (x1_j, x2_j) */
+  const float* bias;        /* [N] (SWIGLU: interleaved like W) */
+  const float* in_part;     /* optional f32 [M, 32] partial sums of squares */
+  int32_t in_nparts, in_dim;
+  const float* sp;          /* f32 [M / T, sp_ld] per-sample shift.W^T + bias vectors (with in_part) */
+  int32_t sp_ld;
+  int32_t H, hd;            /* QKV */
+  const float* cos;         /* f32 (T, hd) or NULL */
+  const float* sin;
+  const float* qn_w;        /* f32 (hd) q_norm / k_norm weights or NULL */
+  const float* kn_w;
+  void* q;                  /* bf16 (M/T, H, T, hdp), hdp = hd rounded up to 16 */
+  void* k;
+  void* vt;                 /* bf16 (M/T, H, hdv, T), hdv = hd + 1 rounded up to 16 */
+  void* out_bf16;           /* SWIGLU: bf16 [M, ldo], N / 2 columns written */
+  int32_t ldo;
+  float* X;                 /* GATED_RESIDUAL: f32 [M, N] residual stream, updated in place */
+  const float* mod;         /* f32 [M / T, mod_ld] adaLN output */
+  int32_t mod_ld, gate_off;
+  const float* nx_w;        /* optional f32 [N]: weight of the RMSNorm that follows */
+  int32_t nx_scale_off;     /* column of its adaLN scale in mod */
+  void* nx_A;               /* bf16 [M, N]: x_new * nx_w * (1 + scale) */
+  float* nx_part;           /* f32 [M, 32]: partial sums of x_new^2, nparts_out slots used */
+  int32_t nparts_out;       /* written by the call */
+} vavae_epilogue_test_t;
+int vavae_test_gemm_epilogue(vavae_epilogue_test_t* t, void* stream);
+
 /* 1: GEMMs use the CTA-pair kernel (cluster of 2, tcgen05 cta_group::2, M = 256 per pair) where the problem
  * allows it; 0: always the single-CTA kernel.  Process-wide; default set by the engine. */
 int vavae_set_gemm_two_cta(int on);
@@ -146,6 +207,28 @@ int vavae_set_gemm_two_cta(int on);
  * number of model rows with CUDA events on `stream`; returns mean milliseconds per launch in *ms. */
 int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters, float* ms, double* work,
                       void* stream);
+
+/* ===== SDE sampler update =====================================================
+ * Replaces the elementwise arithmetic of one step of Sampler.sample_sde (transport/integrators.py:30-49 Euler-Maruyama /
+ * Heun, transport/transport.py:306-334 drift and last step) for path_type "Linear" with a velocity model: the drift
+ * v + diffusion(t) * score(v, x, t), the score from the velocity (transport/path.py:70-84) and the state update in ONE
+ * pass over the latents instead of ~10 elementwise tensor ops.  The batch shares one time, so the coefficients are host
+ * scalars (computed by the caller exactly as the reference computes them, in fp32).  The noise `w` is drawn by the
+ * caller, which keeps the reference's RNG stream.  Modes: 0 Euler-Maruyama step; 1 Heun x-hat; 2 Heun stage 1 (out =
+ * predictor state, out2 = k1); 3 Heun stage 2; 4 last step "Mean"; 5 "Tweedie"; 6 "Euler".  Stateless: needs no engine. */
+typedef struct vavae_sde_update {
+  int32_t mode;
+  const float* x;    /* state the drift is evaluated at (n elements) */
+  const float* v;    /* model output at x (modes 0, 2-6) */
+  const float* w;    /* standard normal noise (modes 0, 1) */
+  const float* k1;   /* mode 3: stage-1 drift */
+  const float* xh;   /* mode 3: x-hat */
+  float* out;
+  float* out2;       /* mode 2: k1 */
+  int64_t n;
+  float t, dt, diffusion, var, sqrt_2diffusion, sqrt_dt, c0, c1;
+} vavae_sde_update_t;
+int vavae_sde_update(const vavae_sde_update_t* u, void* stream);
 
 /* ===== VA-VAE decode path =====================================================
  * Replaces, for inference, AutoencoderKL.decode (LightningDiT/tokenizer/autoencoder.py:490-493: post_quant_conv ->

@@ -26,6 +26,32 @@ def test_ema_preferred_and_module_prefix_stripped(tmp_path):
     # no 'ema' -> 'model'; neither -> bare state_dict
     assert C.select_weights({"model": {"a": 1}}) == {"a": 1}
     assert C.select_weights({"module.a": 1}) == {"a": 1}
+    # only a LEADING 'module.' is DDP's prefix
+    assert C.select_weights({"module.blocks.0.submodule.w": 1}) == {"blocks.0.submodule.w": 1}
+
+
+def test_sampling_loader_is_strict_like_the_reference(tmp_path):
+    """inference.py:91 calls load_state_dict strictly: a checkpoint of another configuration must raise, not sample from
+    partly random weights; strict=False is the opt-in fine-tuning behaviour (train.py:275-301)."""
+    import argparse
+    import pytest
+    m = V.LightningDiT(**KW)
+    sd = _rand_sd(m, 4)
+    sd.pop("blocks.0.attn.proj.bias")
+    path = tmp_path / "partial.pt"
+    torch.save({"ema": sd}, path)
+    with pytest.raises(RuntimeError, match="Missing key"):
+        C.load_checkpoint(m, str(path))
+    C.load_checkpoint(m, str(path), strict=False, verbose=False)
+    assert torch.equal(m.state_dict()["blocks.0.attn.qkv.weight"], sd["blocks.0.attn.qkv.weight"])
+    # a pickle carrying arbitrary objects is refused unless the caller says it is trusted
+    full = _rand_sd(m, 5)
+    bad = tmp_path / "with_args.pt"
+    torch.save({"ema": full, "args": argparse.Namespace(lr=1e-4)}, bad)
+    with pytest.raises(RuntimeError, match="trust_pickle"):
+        C.load_checkpoint(m, str(bad))
+    C.load_checkpoint(m, str(bad), trust_pickle=True)
+    assert torch.equal(m.state_dict()["pos_embed"], full["pos_embed"])
 
 
 def test_shape_checked_partial_load_and_patch_embed_special_case():

@@ -32,7 +32,7 @@ def _worker(rank, world, port, n, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [8, 7])
+@pytest.mark.parametrize("n", [8, 7, 1])      # even, ragged, and n < world size (rank 1 holds an empty shard)
 def test_sharded_sampling_world2_equals_single_process(tmp_path, n):
     import socket
     with socket.socket() as s:
@@ -45,3 +45,14 @@ def test_sharded_sampling_world2_equals_single_process(tmp_path, n):
     z = torch.randn(n, 4, 4, 4, generator=g)
     y = torch.randint(0, 31, (n,), generator=torch.Generator().manual_seed(4321))
     assert torch.equal(out, _stand_in_sampler(z, y))
+
+
+def test_shard_ranges_cover_every_sample_exactly_once():
+    from va_vae_b200.dist import shard_range
+    for n in (0, 1, 7, 128, 1024, 1031):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,9 +1,12 @@
 """Host-side mirror of the reference interface (no GPU): state_dict contract, registry, transport rules,
 time grids, the generic fixed-grid loop, sharding helpers."""
+import os
+
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, rel_l2
+import va_vae_b200 as V
+from conftest import GOLDEN_CASES, ROOT, rel_l2
 from oracle import lightningdit_oracle as O
 
 
@@ -115,3 +118,75 @@ def test_shard_ranges_cover_everything():
     z, y = torch.randn(3, 2, 4, 4), torch.tensor([1, 2, 3])
     zz, yy = build_cfg_batch(z, y, 31)
     assert torch.equal(zz[:3], zz[3:]) and yy.tolist() == [1, 2, 3, 31, 31, 31]
+
+
+def test_engine_label_and_shape_validation_on_the_host():
+    """Engine._labels: host labels are range-checked like nn.Embedding (lightningdit.py:168) and every entry point
+    insists on y of shape (batch,) -- no GPU needed for the checks themselves."""
+    import pytest
+    from va_vae_b200.engine import Engine
+    eng = Engine.__new__(Engine)
+    eng.config = dict(label_rows=32)
+    eng.device = torch.device("cpu")
+    assert eng._labels(torch.tensor([0, 31], dtype=torch.int32), 2).dtype == torch.int64
+    for bad in (torch.tensor([0, 32]), torch.tensor([-1, 3])):
+        with pytest.raises(IndexError, match="index out of range"):
+            eng._labels(bad, 2)
+    with pytest.raises(ValueError):
+        eng._labels(torch.tensor([1]), 2)
+    with pytest.raises(ValueError):
+        eng._labels(torch.zeros(2, 1, dtype=torch.long), 2)
+    with pytest.raises(RuntimeError):
+        eng._labels(torch.tensor([0.0, 1.0]), 2)
+
+
+def test_engine_is_invalidated_by_weight_updates_that_bypass_the_version_counter():
+    m = V.LightningDiT(input_size=4, patch_size=1, in_channels=4, hidden_size=32, depth=1, num_heads=2, num_classes=3,
+                       use_swiglu=True, use_rope=True, use_rmsnorm=True)
+    key = m._weights_key()
+    m._engine_key = key
+    m.load_state_dict(m.state_dict())
+    assert m._engine_key is None                      # load_state_dict invalidates
+    key = m._weights_key()
+    m._engine_key = key
+    m.blocks[0].attn.qkv.weight.data.mul_(0.5)        # invisible to ._version ...
+    assert m._weights_key() == key
+    m.invalidate_engine()                             # ... hence the explicit hook
+    assert m._engine_key is None
+    m._engine_key = key
+    m.feat_rope.freqs_cos.add_(1.0)                   # buffers are part of the key
+    assert m._weights_key() != key
+    m._engine_key = m._weights_key()
+    m.float()                                         # _apply invalidates
+    assert m._engine_key is None
+
+
+def test_bench_arms_describe_the_same_workload(tmp_path):
+    """Both arms of bench.py print the same config.workload string (the driver compares them), the default workload
+    is the configuration BASELINE.json's metric is quoted on, and the reference arm runs all host threads."""
+    import json
+    import subprocess
+    import sys
+    import bench
+    sys_argv = sys.argv
+    try:
+        sys.argv = ["bench.py"]
+        a = bench.parse()
+    finally:
+        sys.argv = sys_argv
+    assert a.workload == "xl1" and a.points == 250 and a.method == "heun"
+    desc = bench.workload_desc(a, 1)
+    assert "LightningDiT-XL/1" in desc and "n=128 per GPU" in desc and "498 evals" in desc
+    env = dict(os.environ, OMP_NUM_THREADS="1")        # what torchrun exports to every rank
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "s1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    sys.argv = ["bench.py", "--workload", "s1"]
+    try:
+        a = bench.parse()
+    finally:
+        sys.argv = sys_argv
+    assert line["impl"] == "reference" and line["config"]["workload"] == bench.workload_desc(a, 1)
+    assert line["cpu_baseline"]["cores"] == (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["metric"] == bench.METRIC

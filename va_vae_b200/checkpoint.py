@@ -24,7 +24,7 @@ def select_weights(checkpoint: Dict) -> Dict[str, torch.Tensor]:
         weights = checkpoint["model"]
     else:
         weights = checkpoint
-    return {k.replace("module.", ""): v for k, v in weights.items()}
+    return {(k[len("module."):] if k.startswith("module.") else k): v for k, v in weights.items()}
 
 
 def load_weights_with_shape_check(model, checkpoint: Dict, rank: int = 0, verbose: bool = True):
@@ -52,14 +52,36 @@ def load_weights_with_shape_check(model, checkpoint: Dict, rank: int = 0, verbos
     return model
 
 
-def load_checkpoint(model, path: str, map_location="cpu", rank: int = 0, verbose: bool = True):
-    """torch.load(path) -> EMA-first selection -> prefix strip -> shape-checked load into `model`."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
-    return load_weights_with_shape_check(model, {"model": select_weights(ckpt)}, rank=rank, verbose=verbose)
+def _torch_load(path: str, map_location, trust_pickle: bool):
+    """weights_only=True by default: a downloaded .pt is untrusted input and the full unpickler executes code.
+    Training checkpoints that carry non-tensor objects (an argparse Namespace under 'args', optimizer state with
+    custom classes) need trust_pickle=True."""
+    try:
+        return torch.load(path, map_location=map_location, weights_only=True)
+    except Exception as exc:
+        if not trust_pickle:
+            raise RuntimeError(f"{path} cannot be read with weights_only=True ({type(exc).__name__}: {exc}); pass "
+                               "trust_pickle=True if the file comes from a trusted source") from exc
+        return torch.load(path, map_location=map_location, weights_only=False)
+
+
+def load_checkpoint(model, path: str, map_location="cpu", rank: int = 0, verbose: bool = True, strict: bool = True,
+                    trust_pickle: bool = False):
+    """The sampling-path loader (LightningDiT/inference.py:88-93): torch.load -> EMA-first selection -> leading
+    'module.' stripped -> `model.load_state_dict(weights)`, STRICT like the reference, so a checkpoint that does not
+    match the model configuration raises instead of sampling from partly random weights.
+    strict=False gives the fine-tuning behaviour of load_weights_with_shape_check (train.py:275-301): tensors whose
+    shape differs or whose name is unknown are skipped and reported."""
+    ckpt = _torch_load(path, map_location, trust_pickle)
+    weights = select_weights(ckpt)
+    if strict:
+        model.load_state_dict(weights, strict=True)
+        return model
+    return load_weights_with_shape_check(model, {"model": weights}, rank=rank, verbose=verbose)
 
 
 def load_latent_stats(path: str, map_location="cpu") -> Tuple[torch.Tensor, torch.Tensor]:
-    stats = torch.load(path, map_location=map_location, weights_only=False)
+    stats = torch.load(path, map_location=map_location, weights_only=True)
     return stats["mean"], stats["std"]
 
 

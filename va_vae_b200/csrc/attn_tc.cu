@@ -18,7 +18,12 @@
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <atomic>
+
 namespace vv {
+
+bool device_marked(const std::atomic<uint64_t>& mask);
+void mark_device(std::atomic<uint64_t>& mask);
 
 constexpr int AT_BQ = 128;   // queries per work item
 constexpr int AT_BKV = 256;  // keys per step
@@ -526,19 +531,17 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   }
   const size_t smem = (size_t)((g.q_bytes + 1023) & ~1023) + ((g.k_bytes + 1023) & ~1023) + g.v_bytes + sizeof(AtBars) + 1024;
   VV_CHECK(smem <= 227 * 1024, "attention: shared memory budget exceeded");
-  int dev, sms;
-  VV_CUDA(cudaGetDevice(&dev));
-  VV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int sms = num_sms();
   const int n_items = a.B * a.H * cdiv(a.T, AT_BQ);
   const int per_sm = smem <= 113 * 1024 ? 2 : 1;
   const int grid = std::min(n_items, sms * per_sm);
   const bool multi = a.T > AT_BKV;
-  static bool attr_set = false;   // not a stream operation: done once, outside any graph capture
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devices{0};   // per device; not a stream operation, safe during graph capture
+  if (!device_marked(attr_devices)) {
     VV_CUDA(cudaFuncSetAttribute(k_attention_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VV_CUDA(cudaFuncSetAttribute(k_attention_tc<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VV_CUDA(cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    mark_device(attr_devices);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -74,6 +74,10 @@ struct F32GemmArgs {
   RowMap rm;
   float* C2;
   bf16* C2h;
+  // label range check (nn.Embedding raises on an out-of-range index; a kernel cannot): rows of `table`, and a device
+  // flag that is set when a label falls outside [0, label_rows) - the read is clamped to row 0, never out of bounds
+  int label_rows;
+  int* err_flag;
 };
 void launch_gemm_f32(const F32GemmArgs& a, cudaStream_t s);
 
@@ -90,7 +94,7 @@ struct EmbedArgs {
 void launch_patch_embed(const EmbedArgs& a, cudaStream_t s);
 
 void launch_cond_combine(const float* temb, const float* table, const int64_t* labels, RowMap rm, float* sc_f, bf16* sc_h,
-                         int rows, int D, cudaStream_t s);
+                         int rows, int D, int label_rows, int* err_flag, cudaStream_t s);
 void launch_patchify_split3(const float* x, bf16* out, int rows, int C, int img, int p, int T, RowMap rm, cudaStream_t s);
 void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowMap rm, cudaStream_t s);
 
@@ -166,8 +170,30 @@ struct OdeArgs {
   int channels;
   float dt;
   int stage;
+  int skip_uncond;  // 1: the unconditional forward of this (gated-off) evaluation was not run - rows >= n of `v` are stale
+                    // and rows >= n of the state follow the conditional velocity (they never feed back, lightningdit.py:425)
 };
 void launch_ode_update(const OdeArgs& a, cudaStream_t s);
+
+// Elementwise update of the SDE sampler (transport/integrators.py:30-49, transport/transport.py:306-334) for the linear
+// path with a velocity model: the batch shares one time, so every coefficient is a host scalar.
+//   drift(v, x) = v + diff * ((t * v - x) / var)                       (path.py:45-84 with alpha = t, sigma = 1 - t)
+// mode 0  Euler-Maruyama : out = (x + drift(v,x) * dt) + s2d * (w * sqdt)
+// mode 1  Heun, x-hat    : out = x + s2d * (w * sqdt)
+// mode 2  Heun, stage 1  : out2 = k1 = drift(v, x) ; out = x + dt * k1           (x = x-hat)
+// mode 3  Heun, stage 2  : out = xh + (0.5 * dt) * (k1 + drift(v, x))            (x = stage-1 output, xh = x-hat)
+// mode 4  last step Mean : out = x + drift(v, x) * dt                            (dt = last_step_size)
+// mode 5  Tweedie        : out = x / t + ((1-t)^2 / t) * ((t * v - x) / var)
+// mode 6  last step Euler: out = x + v * dt
+// Every operation is a separately rounded fp32 op in the reference's order (no FMA contraction).
+struct SdeArgs {
+  int mode;
+  const float *x, *v, *w, *k1, *xh;
+  float *out, *out2;
+  size_t n;
+  float t, dt, diff, var, s2d, sqdt, c0, c1;   // c0, c1: Tweedie 1/.. coefficients (alpha, sigma^2/alpha)
+};
+void launch_sde_update(const SdeArgs& a, cudaStream_t s);
 
 // ---- adaptive RK (dopri5) helpers
 struct RkCombineArgs {

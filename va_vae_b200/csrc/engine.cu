@@ -46,6 +46,8 @@ struct vavae_engine {
   std::vector<void*> owned;  // everything cudaMalloc'ed by the engine
   uint64_t bytes = 0;
   LaunchCounter counter;
+  uint64_t fwd_rows = 0;     // model rows pushed through the layer stack since creation (executed forwards)
+  int* err_flag = nullptr;   // device flag: a label outside [0, label_rows) was seen (vavae_device_status)
   // live per-kernel profiling (bench.py roofline): CUDA event pairs around every launch of one kernel class
   int prof_kernel = -1;
   std::vector<cudaEvent_t> prof_ev;  // pairs: [2i] start, [2i+1] stop
@@ -91,6 +93,7 @@ struct vavae_engine {
   struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     size_t nodes = 0;
+    uint64_t rows = 0;   // model rows one replay pushes through the layer stack
   };
   std::map<std::string, GraphEntry> graphs;
   std::set<std::string> graph_warm;
@@ -437,6 +440,7 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
   e->cbuf = e->alloc<float>((size_t)R * D);
   e->mod = e->alloc<float>((size_t)R * e->NMx);
   e->st = e->alloc<float>(4);
+  e->err_flag = e->alloc<int>(1, true);
   if (e->fp32) {
     e->sc_f = e->alloc<float>((size_t)R * D);
     e->A_f = e->alloc<float>(M * D);
@@ -529,7 +533,7 @@ static void conditioning(vavae_engine* e, int rows, const RowMap& rm, const floa
     gemm32(e->th, D, e->W("t_embedder.mlp.2.weight").d, e->W("t_embedder.mlp.2.bias").d, e->cbuf, D, 1, D, D,
            F32_EPI_NONE, s);
     launch_cond_combine(e->cbuf, e->W("y_embedder.embedding_table.weight").d, y, rm, e->fp32 ? e->sc_f : nullptr,
-                        e->fp32 ? nullptr : e->sc_h, rows, D, s);
+                        e->fp32 ? nullptr : e->sc_h, rows, D, e->cfg.label_rows, e->err_flag, s);
   } else {
   launch_tfreq(t, e->W("t_embedder.freqs").d, e->tf, rows, rm, s);
   gemm32(e->tf, 256, e->W("t_embedder.mlp.0.weight").d, e->W("t_embedder.mlp.0.bias").d, e->th, D, rows, D, 256,
@@ -540,6 +544,7 @@ static void conditioning(vavae_engine* e, int rows, const RowMap& rm, const floa
   g.C = e->cbuf; g.ldc = D; g.M = rows; g.N = D; g.K = D; g.epi = F32_EPI_ADD_LABEL_SILU;
   g.table = e->W("y_embedder.embedding_table.weight").d; g.labels = y; g.rm = rm;
   g.C2 = e->fp32 ? e->sc_f : nullptr; g.C2h = e->fp32 ? nullptr : e->sc_h;
+  g.label_rows = e->cfg.label_rows; g.err_flag = e->err_flag;
   launch_gemm_f32(g, s);
   }
   // every adaLN modulation of the network in one GEMM: mod[rows, NM]
@@ -558,6 +563,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
   const int M = rows * T;
   const vavae_config_t& c = e->cfg;
   VV_CHECK(rows <= e->chunk_rows, "forward_chunk: chunk larger than workspace");
+  e->fwd_rows += (uint64_t)rows;
   const int Cpp = e->C * e->p * e->p;
   if (!e->fp32 && (3 * Cpp) % 8 == 0) {
     // patch embed on the tensor cores: split-bf16 patches x [W_hi | W_hi | W_lo], fp32-grade; epilogue adds bias + pos
@@ -740,6 +746,13 @@ static void forward_pairs(vavae_engine* e, const float* x, const float* t, int t
   }
 }
 
+// forward of the n conditional rows only (model row b reads latent row b, label b, writes velocity row b): what is left
+// of forward_pairs when the CFG-interval gate discards the unconditional half (lightningdit.py:436-439)
+static void forward_cond_only(vavae_engine* e, const float* x, const float* t, int t_stride, const int64_t* y, float* out,
+                              int n, cudaStream_t s) {
+  forward_plain(e, x, t, t_stride, y, out, n, s);
+}
+
 static void ensure_state(vavae_engine* e, int rows) {
   if (rows <= e->state_rows) return;
   const size_t per = (size_t)e->C * e->img * e->img;
@@ -777,7 +790,7 @@ static void run_graphed(vavae_engine* e, const std::string& key, const std::func
     }
     if (!e->gstream) VV_CUDA(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
-    const uint64_t before = e->counter.n;
+    const uint64_t before = e->counter.n, rows_before = e->fwd_rows;
     VV_CUDA(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
     try {
       launch(e->gstream);
@@ -789,18 +802,24 @@ static void run_graphed(vavae_engine* e, const std::string& key, const std::func
     VV_CUDA(cudaStreamEndCapture(e->gstream, &graph));
     vavae_engine::GraphEntry ge;
     ge.nodes = (size_t)(e->counter.n - before);
+    ge.rows = e->fwd_rows - rows_before;
     e->counter.n = before;  // captured launches did not execute; replays are counted below
+    e->fwd_rows = rows_before;
     VV_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
     VV_CUDA(cudaGraphDestroy(graph));
     it = e->graphs.emplace(key, ge).first;
   }
   VV_CUDA(cudaGraphLaunch(it->second.exec, s));
   e->counter.n += it->second.nodes;
+  e->fwd_rows += it->second.rows;
 }
 
 static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const float* t_grid, int n_points, int method,
                        int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start, int cfg_channels,
-                       float* out_final, float* out_trace, int batch, cudaStream_t s) {
+                       float* out_final, float* out_trace, int batch, int flags, cudaStream_t s) {
+  // VAVAE_SAMPLE_SKIP_DISCARDED: an evaluation at t < cfg_interval_start keeps only the conditional output
+  // (lightningdit.py:436-439 computes the unconditional forward and throws it away) - run the n conditional rows only
+  const bool skip_discarded = (flags & VAVAE_SAMPLE_SKIP_DISCARDED) && use_cfg && cfg_interval;
   VV_CHECK(n_points >= 2, "sample_ode: need at least two grid points");
   VV_CHECK(method == VAVAE_ODE_EULER || method == VAVAE_ODE_HEUN, "sample_ode: method must be euler or heun (fixed grid)");
   VV_CHECK(!use_cfg || batch % 2 == 0, "sample_ode: CFG batch must be even (inference.py:205-211)");
@@ -826,29 +845,35 @@ static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const 
   }
   if (xs != z) VV_CUDA(cudaMemcpyAsync(xs, z, state_bytes, cudaMemcpyDeviceToDevice, s));
   int eval = 0;
-  auto eval_model = [&](const float* xin, int tidx) {
+  // returns true when only the conditional rows were evaluated (same fp32 compare as the device-side gate)
+  auto eval_model = [&](const float* xin, int tidx) -> bool {
+    const bool cond_only = skip_discarded && t_grid[tidx] < cfg_interval_start;
     if (graphed) {
       // the evaluation time goes through a fixed device scalar so the captured kernels never change
       VV_CUDA(cudaMemcpyAsync(e->st, e->tgrid_dev + tidx, sizeof(float), cudaMemcpyDeviceToDevice, s));
-      const std::string key = std::string("S") + (use_cfg ? "c" : "p") + (xin == e->sxp ? "1" : "0") + "_" + std::to_string(batch);
+      const std::string key = std::string("S") + (use_cfg ? (cond_only ? "h" : "c") : "p") + (xin == e->sxp ? "1" : "0") + "_" +
+                              std::to_string(batch);
       run_graphed(e, key, [&](cudaStream_t gs) {
-        if (use_cfg) forward_pairs(e, xin, e->st, 0, yy, e->sv, batch / 2, gs);
+        if (cond_only) forward_cond_only(e, xin, e->st, 0, yy, e->sv, batch / 2, gs);
+        else if (use_cfg) forward_pairs(e, xin, e->st, 0, yy, e->sv, batch / 2, gs);
         else forward_plain(e, xin, e->st, 0, yy, e->sv, batch, gs);
       }, s);
-      return;
+      return cond_only;
     }
     const float* tp = e->tgrid_dev + tidx;  // every row uses the same time: t_stride = 0
-    if (use_cfg) forward_pairs(e, xin, tp, 0, yy, e->sv, batch / 2, s);
+    if (cond_only) forward_cond_only(e, xin, tp, 0, yy, e->sv, batch / 2, s);
+    else if (use_cfg) forward_pairs(e, xin, tp, 0, yy, e->sv, batch / 2, s);
     else forward_plain(e, xin, tp, 0, yy, e->sv, batch, s);
+    return cond_only;
   };
   OdeArgs o;
   o.v = e->sv; o.x = xs; o.xp = e->sxp; o.k1 = e->sk1; o.rows = batch; o.C = e->C; o.HW = e->img * e->img;
   o.use_cfg = use_cfg; o.scale = cfg_scale; o.interval = cfg_interval; o.start = cfg_interval_start;
-  o.channels = cfg_channels;
+  o.channels = cfg_channels; o.skip_uncond = 0;
   for (int j = 0; j + 1 < n_points; ++j) {
     const float dt = t_grid[j + 1] - t_grid[j];  // fp32, like torchdiffeq's t1 - t0 on fp32 tensors
     o.dt = dt;
-    eval_model(xs, j);
+    o.skip_uncond = eval_model(xs, j) ? 1 : 0;
     o.t = e->tgrid_dev + j;
     o.trace = out_trace ? out_trace + (size_t)(eval++) * batch * per : nullptr;
     o.stage = method == VAVAE_ODE_EULER ? 0 : 1;
@@ -858,7 +883,7 @@ static void sample_ode(vavae_engine* e, const float* z, const int64_t* y, const 
       launch_ode_update(o, s);
     }
     if (method == VAVAE_ODE_HEUN) {
-      eval_model(e->sxp, j + 1);
+      o.skip_uncond = eval_model(e->sxp, j + 1) ? 1 : 0;
       o.t = e->tgrid_dev + j + 1;
       o.trace = out_trace ? out_trace + (size_t)(eval++) * batch * per : nullptr;
       o.stage = 2;
@@ -1139,18 +1164,19 @@ int vavae_forward_with_cfg(vavae_engine_t* e, const float* x, const float* t, co
 
 int vavae_sample_ode(vavae_engine_t* e, const float* z, const int64_t* y, const float* t_grid, int n_points, int method,
                      int use_cfg, float cfg_scale, int cfg_interval, float cfg_interval_start, int cfg_channels,
-                     float* out_final, float* out_trace, int batch, void* stream) {
+                     float* out_final, float* out_trace, int batch, int flags, void* stream) {
   VV_API_BEGIN(e)
   VV_CHECK(e && e->finalized, "engine not finalized");
   VV_CHECK(batch > 0 && z && y && t_grid && out_final, "null / empty argument");
   sample_ode(e, z, y, t_grid, n_points, method, use_cfg, cfg_scale, cfg_interval, cfg_interval_start, cfg_channels,
-             out_final, out_trace, batch, (cudaStream_t)stream);
+             out_final, out_trace, batch, flags, (cudaStream_t)stream);
   VV_API_END()
 }
 
 int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t* y_host, const float* t_grid,
                           int n_points, int method, int use_cfg, float cfg_scale, int cfg_interval,
-                          float cfg_interval_start, int cfg_channels, float* out_final_host, int batch, void* stream) {
+                          float cfg_interval_start, int cfg_channels, float* out_final_host, int batch, int flags,
+                          void* stream) {
   VV_API_BEGIN(e)
   VV_CHECK(e && e->finalized, "engine not finalized");
   VV_CHECK(batch > 0 && z_host && y_host && t_grid && out_final_host, "null / empty argument");
@@ -1160,9 +1186,15 @@ int vavae_sample_ode_host(vavae_engine_t* e, const float* z_host, const int64_t*
   VV_CUDA(cudaMemcpyAsync(e->sx, z_host, bytes, cudaMemcpyHostToDevice, s));
   VV_CUDA(cudaMemcpyAsync(e->sy, y_host, (size_t)batch * sizeof(int64_t), cudaMemcpyHostToDevice, s));
   sample_ode(e, e->sx, e->sy, t_grid, n_points, method, use_cfg, cfg_scale, cfg_interval, cfg_interval_start,
-             cfg_channels, e->sx, nullptr, batch, s);
+             cfg_channels, e->sx, nullptr, batch, flags, s);
   VV_CUDA(cudaMemcpyAsync(out_final_host, e->sx, bytes, cudaMemcpyDeviceToHost, s));
+  int bad = 0;
+  VV_CUDA(cudaMemcpyAsync(&bad, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
   VV_CUDA(cudaStreamSynchronize(s));
+  if (bad) {
+    VV_CUDA(cudaMemsetAsync(e->err_flag, 0, sizeof(int), s));
+    throw Error("index out of range in self (label outside [0, label_rows) of y_embedder.embedding_table)");
+  }
   VV_API_END()
 }
 
@@ -1178,7 +1210,22 @@ int vavae_sample_dopri5(vavae_engine_t* e, const float* z, const int64_t* y, dou
   VV_API_END()
 }
 
+int vavae_device_status(vavae_engine_t* e, void* stream) {
+  VV_API_BEGIN(e)
+  VV_CHECK(e && e->finalized, "engine not finalized");
+  cudaStream_t s = (cudaStream_t)stream;
+  int bad = 0;
+  VV_CUDA(cudaMemcpyAsync(&bad, e->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  VV_CUDA(cudaStreamSynchronize(s));
+  if (bad) {
+    VV_CUDA(cudaMemsetAsync(e->err_flag, 0, sizeof(int), s));
+    throw Error("index out of range in self (label outside [0, label_rows) of y_embedder.embedding_table)");
+  }
+  VV_API_END()
+}
+
 uint64_t vavae_launch_count(const vavae_engine_t* e) { return e ? e->counter.n : 0; }
+uint64_t vavae_forward_rows(const vavae_engine_t* e) { return e ? e->fwd_rows : 0; }
 uint64_t vavae_device_bytes(const vavae_engine_t* e) { return e ? e->bytes : 0; }
 
 int vavae_profile_begin(vavae_engine_t* e, const char* kernel) {
@@ -1235,6 +1282,82 @@ int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void
     a.q = (const bf16*)q; a.k = (const bf16*)k; a.vt = (const bf16*)vt; a.out = (bf16*)out;
     a.B = B; a.H = H; a.T = T; a.hd = hd; a.hdp = ((hd + 15) / 16) * 16; a.hdv = attention_hdv(hd);
     launch_attention_tc(a, (cudaStream_t)stream);
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return 1;
+  }
+}
+
+// One launch of the production tcgen05 GEMM with one of its fused epilogues on caller-provided operands (tests only).
+int vavae_test_gemm_epilogue(vavae_epilogue_test_t* t, void* stream) {
+  float* rope_cs = nullptr;
+  try {
+    vv::g_counter = nullptr;
+    VV_CHECK(t && t->A && t->W && t->M > 0 && t->N > 0 && t->K > 0 && t->T > 0, "test_gemm_epilogue: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int epi = t->kind == VAVAE_EPI_QKV ? TC_EPI_QKV : (t->kind == VAVAE_EPI_SWIGLU ? TC_EPI_SWIGLU : TC_EPI_GATED_RESIDUAL);
+    VV_CHECK(t->kind >= VAVAE_EPI_QKV && t->kind <= VAVAE_EPI_GATED_RESIDUAL, "test_gemm_epilogue: unknown kind");
+    TcGemmArgs a = tc_args((const bf16*)t->A, t->K, (const bf16*)t->W, t->K, t->M, t->N, t->K, epi, t->bias);
+    a.T = t->T;
+    if (t->in_part) {
+      VV_CHECK(t->kind != VAVAE_EPI_GATED_RESIDUAL && t->sp, "test_gemm_epilogue: fused-norm consumer needs sp and kind 0/1");
+      a.in_part = t->in_part; a.in_nparts = t->in_nparts; a.in_dim = t->in_dim; a.sp = t->sp; a.sp_ld = t->sp_ld;
+    }
+    if (t->kind == VAVAE_EPI_QKV) {
+      VV_CHECK(t->q && t->k && t->vt && t->H > 0 && t->hd > 0 && t->N == 3 * t->H * t->hd, "test_gemm_epilogue: qkv outputs");
+      a.q = (bf16*)t->q; a.k = (bf16*)t->k; a.vt = (bf16*)t->vt; a.cos = t->cos; a.sin = t->sin; a.qn_w = t->qn_w; a.kn_w = t->kn_w;
+      a.qk_rms = 1; a.H = t->H; a.hd = t->hd; a.hdp = ((t->hd + 15) / 16) * 16; a.hdv = attention_hdv(t->hd);
+      if (t->cos && t->sin && t->hd % 2 == 0) {
+        // same repack as vavae_finalize: one (cos, sin) pair per rotation pair when the tables repeat each frequency twice
+        const size_t nel = (size_t)t->T * t->hd;
+        std::vector<float> hc(nel), hs(nel), cs(nel);
+        VV_CUDA(cudaStreamSynchronize(s));
+        VV_CUDA(cudaMemcpy(hc.data(), t->cos, nel * 4, cudaMemcpyDeviceToHost));
+        VV_CUDA(cudaMemcpy(hs.data(), t->sin, nel * 4, cudaMemcpyDeviceToHost));
+        bool paired = true;
+        for (size_t i = 0; i < nel && paired; i += 2) paired = hc[i] == hc[i + 1] && hs[i] == hs[i + 1];
+        if (paired) {
+          for (size_t i = 0; i < nel; i += 2) { cs[i] = hc[i]; cs[i + 1] = hs[i]; }
+          VV_CUDA(cudaMalloc(&rope_cs, nel * 4));
+          VV_CUDA(cudaMemcpy(rope_cs, cs.data(), nel * 4, cudaMemcpyHostToDevice));
+          a.rope_cs = rope_cs;
+        }
+      }
+    } else if (t->kind == VAVAE_EPI_SWIGLU) {
+      VV_CHECK(t->out_bf16 && t->ldo >= t->N / 2, "test_gemm_epilogue: swiglu output");
+      a.out = t->out_bf16; a.ldo = t->ldo;
+    } else {
+      VV_CHECK(t->X && t->mod, "test_gemm_epilogue: gated residual needs X and mod");
+      a.out = t->X; a.ldo = t->N; a.mod = t->mod; a.mod_ld = t->mod_ld; a.gate_off = t->gate_off;
+      if (t->nx_w) {
+        VV_CHECK(t->nx_A && t->nx_part, "test_gemm_epilogue: next-norm outputs");
+        a.nx_w = t->nx_w; a.nx_scale_off = t->nx_scale_off; a.nx_A = (bf16*)t->nx_A; a.nx_part = t->nx_part;
+        t->nparts_out = 2 * cdiv(t->N, gemm_tc_pick_bn(a));
+      }
+    }
+    launch_gemm_tc(a, s);
+    if (rope_cs) {
+      VV_CUDA(cudaStreamSynchronize(s));
+      cudaFree(rope_cs);
+    }
+    return 0;
+  } catch (const std::exception& ex) {
+    if (rope_cs) cudaFree(rope_cs);
+    g_err = ex.what();
+    return 1;
+  }
+}
+
+int vavae_sde_update(const vavae_sde_update_t* u, void* stream) {
+  try {
+    vv::g_counter = nullptr;
+    VV_CHECK(u, "null argument");
+    SdeArgs a;
+    a.mode = u->mode; a.x = u->x; a.v = u->v; a.w = u->w; a.k1 = u->k1; a.xh = u->xh; a.out = u->out; a.out2 = u->out2;
+    a.n = (size_t)u->n; a.t = u->t; a.dt = u->dt; a.diff = u->diffusion; a.var = u->var; a.s2d = u->sqrt_2diffusion;
+    a.sqdt = u->sqrt_dt; a.c0 = u->c0; a.c1 = u->c1;
+    launch_sde_update(a, (cudaStream_t)stream);
     return 0;
   } catch (const std::exception& ex) {
     g_err = ex.what();

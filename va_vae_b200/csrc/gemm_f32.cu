@@ -73,7 +73,12 @@ __global__ void __launch_bounds__(256) k_gemm_f32(F32GemmArgs a) {
     int lab_row = 0;
     if (a.epi == F32_EPI_ADD_LABEL_SILU) {
       int seg = gm / a.rm.seg_rows, ii = gm - seg * a.rm.seg_rows;
-      lab_row = (int)a.labels[a.rm.y_off[seg] + ii];
+      const int64_t lab = a.labels[a.rm.y_off[seg] + ii];
+      if (lab < 0 || lab >= (int64_t)a.label_rows) {
+        if (a.err_flag) *a.err_flag = 1;   // surfaced by vavae_device_status(); the read is clamped
+      } else {
+        lab_row = (int)lab;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -9,8 +9,11 @@
 #include "gemm_tc.cuh"
 #include "tc_ptx.cuh"
 
-#include <mutex>
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 namespace vv {
 
@@ -32,8 +35,39 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Descriptors are cached per (pointer, shape, box, swizzle): a sampler step re-launches the same ~10 GEMM shapes on the
+// same workspace pointers tens of thousands of times, and cuTensorMapEncodeTiled is a driver call.
+struct TmapKey {
+  uint64_t v[12];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 12; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+template <typename F>
+static CUtensorMap cached_tmap(const TmapKey& key, F&& encode) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  const CUtensorMap m = encode();
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, m);
+  return m;
+}
+
 CUtensorMap make_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
                               uint32_t box_inner, uint32_t box_outer) {
+  const TmapKey key = {{2, (uint64_t)(uintptr_t)base, inner, outer, row_pitch_bytes, box_inner, box_outer, 128, 0, 0, 0, 0}};
+  return cached_tmap(key, [&] {
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_pitch_bytes};
@@ -45,9 +79,12 @@ CUtensorMap make_tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, 
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(2d) failed with code " + std::to_string((int)r));
   return m;
+  });
 }
 CUtensorMap make_tmap_3d_bf16(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                               uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  const TmapKey key = {{3, (uint64_t)(uintptr_t)base, d0, d1, d2, pitch1_bytes, pitch2_bytes, b0, b1, b2, 128, 0}};
+  return cached_tmap(key, [&] {
   CUtensorMap m;
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
@@ -60,10 +97,13 @@ CUtensorMap make_tmap_3d_bf16(const void* base, uint64_t d0, uint64_t d1, uint64
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(3d) failed with code " + std::to_string((int)r));
   return m;
+  });
 }
 
 CUtensorMap make_tmap_nhwc_bf16(const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t bw,
                                 uint32_t bh, uint32_t bn) {
+  const TmapKey key = {{4, (uint64_t)(uintptr_t)base, C, W, H, N, bw, bh, bn, 0, 0, 0}};
+  return cached_tmap(key, [&] {
   CUtensorMap m;
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {C * 2, C * W * 2, C * W * H * 2};
@@ -76,10 +116,14 @@ CUtensorMap make_tmap_nhwc_bf16(const void* base, uint64_t C, uint64_t W, uint64
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // out-of-bounds elements read as zero = the conv padding
   if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(nhwc) failed with code " + std::to_string((int)r));
   return m;
+  });
 }
 
 CUtensorMap make_tmap_3d_bf16_sw(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                                  uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes) {
+  const TmapKey key = {{5, (uint64_t)(uintptr_t)base, d0, d1, d2, pitch1_bytes, pitch2_bytes, b0, b1, b2,
+                        (uint64_t)swizzle_bytes, 0}};
+  return cached_tmap(key, [&] {
   CUtensorMap m;
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
@@ -95,6 +139,7 @@ CUtensorMap make_tmap_3d_bf16_sw(const void* base, uint64_t d0, uint64_t d1, uin
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(3d, swizzle) failed with code " + std::to_string((int)r));
   return m;
+  });
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -1059,15 +1104,30 @@ bool pdl_enabled(cudaStream_t s) {
   return st == cudaStreamCaptureStatusNone;
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev;
-    VV_CUDA(cudaGetDevice(&dev));
-    VV_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return g_num_sms;
+// Per-device state: function attributes and the SM count belong to a device (context), not to the process - a second
+// engine on another GPU of the same process needs its own opt-in to > 48 KB of dynamic shared memory.
+int current_device() {
+  int dev;
+  VV_CUDA(cudaGetDevice(&dev));
+  VV_CHECK(dev >= 0 && dev < 64, "device index >= 64 not supported");
+  return dev;
 }
+int num_sms() {
+  static std::atomic<int> sms[64];
+  const int dev = current_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    VV_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    sms[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+// One bit per device in a per-kernel mask.  The bit is set AFTER the attribute call, so a thread that sees it may
+// launch; two threads racing on the first use both set the attribute, which is harmless.
+bool device_marked(const std::atomic<uint64_t>& mask) {
+  return (mask.load(std::memory_order_acquire) >> current_device()) & 1ull;
+}
+void mark_device(std::atomic<uint64_t>& mask) { mask.fetch_or(1ull << current_device(), std::memory_order_acq_rel); }
 
 // 0: always the 1-CTA kernel; 1: CTA pairs only for the GEMMs whose main loop dominates (w12, w3, large-K QKV);
 // 2 (default): CTA pairs wherever the shape allows it.  Measured on B200, whole 250-step sampler, power-capped
@@ -1130,10 +1190,10 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
   if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
   VV_CHECK(nstages >= 2, "gemm_tc: tile too large for shared memory");
   const size_t smem = (size_t)nstages * stage_bytes + fixed;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_devices{0};   // one bit per device, per kernel instantiation
+  if (!device_marked(attr_devices)) {
     VV_CUDA(cudaFuncSetAttribute(k_gemm_tc<EPI, CW, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    mark_device(attr_devices);
   }
   CUtensorMap tmA;
   if (a.conv_taps) {

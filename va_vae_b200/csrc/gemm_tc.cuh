@@ -84,6 +84,9 @@ struct TcAttnArgs {
 };
 void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s);
 bool pdl_enabled(cudaStream_t s);
+// per-device helpers (function attributes and SM counts are per device, not per process)
+int current_device();
+int num_sms();
 // rows of the transposed V tensor: head_dim + one row of ones (row-sum column of P V), rounded up to 16
 int attention_hdv(int hd);
 

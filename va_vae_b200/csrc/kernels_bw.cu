@@ -3,6 +3,8 @@
 // Math follows SURVEY.md Appendix A (reference: LightningDiT/models/lightningdit.py).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace vv {
 
 thread_local LaunchCounter* g_counter = nullptr;
@@ -136,20 +138,25 @@ void launch_tfreq(const float* t, const float* freqs, float* out, int rows, RowM
 // ------------------------------------------------------------------------------------------------
 __global__ void k_cond_combine(const float* __restrict__ temb, const float* __restrict__ table,
                                const int64_t* __restrict__ labels, RowMap rm, float* __restrict__ sc_f,
-                               bf16* __restrict__ sc_h, int rows, int D) {
+                               bf16* __restrict__ sc_h, int rows, int D, int label_rows, int* __restrict__ err_flag) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * D) return;
   int r = idx / D, d = idx - r * D;
   int i;
   int seg = rm_seg(rm, r, i);
-  float v = temb[d] + table[(size_t)labels[rm.y_off[seg] + i] * D + d];
+  int64_t lab = labels[rm.y_off[seg] + i];
+  if (lab < 0 || lab >= (int64_t)label_rows) {   // nn.Embedding would raise: flag it, read row 0 instead of out of bounds
+    if (d == 0 && err_flag) *err_flag = 1;
+    lab = 0;
+  }
+  float v = temb[d] + table[(size_t)lab * D + d];
   float sv = v / (1.0f + expf(-v));
   if (sc_f) sc_f[idx] = sv;
   if (sc_h) sc_h[idx] = __float2bfloat16_rn(sv);
 }
 void launch_cond_combine(const float* temb, const float* table, const int64_t* labels, RowMap rm, float* sc_f, bf16* sc_h,
-                         int rows, int D, cudaStream_t s) {
-  k_cond_combine<<<cdiv(rows * D, 256), 256, 0, s>>>(temb, table, labels, rm, sc_f, sc_h, rows, D);
+                         int rows, int D, int label_rows, int* err_flag, cudaStream_t s) {
+  k_cond_combine<<<cdiv(rows * D, 256), 256, 0, s>>>(temb, table, labels, rm, sc_f, sc_h, rows, D, label_rows, err_flag);
   VV_LAUNCH_CHECK();
 }
 
@@ -519,7 +526,8 @@ __global__ void k_ode_update(OdeArgs a) {
     int c = (int)((idx / HW4) % a.C);
     const bool guided = !(a.interval && (a.t[0] < a.start));
     float4 vc = reinterpret_cast<const float4*>(a.v)[idx];
-    float4 vu = reinterpret_cast<const float4*>(a.v)[idx + half4];
+    const bool no_uncond = a.skip_uncond && !guided;   // host skipped the forward whose output the gate discards
+    float4 vu = no_uncond ? vc : reinterpret_cast<const float4*>(a.v)[idx + half4];
     if (c < a.channels) {
       float4 g = guided ? lerp_cfg(vc, vu, a.scale) : vc;
       vc = g;
@@ -537,6 +545,48 @@ void launch_ode_update(const OdeArgs& a, cudaStream_t s) {
   VV_CHECK(a.HW % 4 == 0, "ode_update: H*W must be a multiple of 4");
   size_t work4 = (size_t)(a.use_cfg ? a.rows / 2 : a.rows) * a.C * (a.HW / 4);
   k_ode_update<<<(unsigned)((work4 + 255) / 256), 256, 0, s>>>(a);
+  VV_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// SDE sampler update (see SdeArgs): one pass, separately rounded fp32 operations in the reference's order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sde_drift(const SdeArgs& a, float v, float x) {
+  const float score = __fdiv_rn(__fsub_rn(__fmul_rn(a.t, v), x), a.var);
+  return __fadd_rn(v, __fmul_rn(a.diff, score));
+}
+__global__ void k_sde_update(SdeArgs a) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < a.n; i += stride) {
+    const float x = a.x[i];
+    float o;
+    switch (a.mode) {
+      case 0: o = __fadd_rn(__fadd_rn(x, __fmul_rn(sde_drift(a, a.v[i], x), a.dt)), __fmul_rn(a.s2d, __fmul_rn(a.w[i], a.sqdt))); break;
+      case 1: o = __fadd_rn(x, __fmul_rn(a.s2d, __fmul_rn(a.w[i], a.sqdt))); break;
+      case 2: {
+        const float k1 = sde_drift(a, a.v[i], x);
+        a.out2[i] = k1;
+        o = __fadd_rn(x, __fmul_rn(a.dt, k1));
+        break;
+      }
+      case 3: o = __fadd_rn(a.xh[i], __fmul_rn(__fmul_rn(0.5f, a.dt), __fadd_rn(a.k1[i], sde_drift(a, a.v[i], x)))); break;
+      case 4: o = __fadd_rn(x, __fmul_rn(sde_drift(a, a.v[i], x), a.dt)); break;
+      case 5: o = __fadd_rn(__fdiv_rn(x, a.c0), __fmul_rn(a.c1, __fdiv_rn(__fsub_rn(__fmul_rn(a.t, a.v[i]), x), a.var))); break;
+      default: o = __fadd_rn(x, __fmul_rn(a.v[i], a.dt)); break;
+    }
+    a.out[i] = o;
+  }
+}
+void launch_sde_update(const SdeArgs& a, cudaStream_t s) {
+  VV_CHECK(a.mode >= 0 && a.mode <= 6 && a.x && a.out, "sde_update: bad arguments");
+  VV_CHECK(a.mode == 1 || a.v, "sde_update: model output missing");
+  VV_CHECK((a.mode != 0 && a.mode != 1) || a.w, "sde_update: noise missing");
+  VV_CHECK(a.mode != 2 || a.out2, "sde_update: k1 output missing");
+  VV_CHECK(a.mode != 3 || (a.k1 && a.xh), "sde_update: Heun stage-2 inputs missing");
+  if (a.n == 0) return;
+  unsigned grid = (unsigned)std::min<size_t>((a.n + 255) / 256, (size_t)148 * 16);
+  k_sde_update<<<grid, 256, 0, s>>>(a);
   VV_LAUNCH_CHECK();
 }
 

@@ -26,17 +26,33 @@ def build_cfg_batch(z: torch.Tensor, y: torch.Tensor, null_label: int):
     return torch.cat([z, z], 0), torch.cat([y, torch.full_like(y, null_label)], 0)
 
 
+def _collective_device(z: torch.Tensor, group, device):
+    """Device the gathered tensors must live on: the caller's choice, else the current CUDA device under NCCL (the
+    noise z is typically generated once on the CPU, while NCCL only moves CUDA tensors), else z's own device."""
+    if device is not None:
+        return torch.device(device)
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return z.device
+
+
 def sample_sharded(sample_local: Callable[[torch.Tensor, torch.Tensor], torch.Tensor], z: torch.Tensor, y: torch.Tensor,
-                   group=None, gather: bool = True) -> torch.Tensor:
+                   group=None, gather: bool = True, device=None) -> torch.Tensor:
     """Shard (z, y) over the ranks of `group`, run `sample_local(z_shard, y_shard) -> latents_shard` on each,
     all-gather the final latents.  `sample_local` wraps Engine.sample_ode (CFG doubling included).
-    Works with any backend (NCCL on the GPU box, gloo in the CPU tests)."""
+    Works with any backend (NCCL on the GPU box, gloo in the CPU tests).  `device`: where the shard results and the
+    gathered tensor live (default: the current CUDA device under NCCL, z's device otherwise); a rank whose shard is
+    empty (n < world size) contributes an empty tensor on that device."""
     if not (dist.is_available() and dist.is_initialized()):
         return sample_local(z, y)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = z.shape[0]
     lo, hi = shard_range(n, rank, world)
-    local = sample_local(z[lo:hi], y[lo:hi]) if hi > lo else z.new_empty((0,) + tuple(z.shape[1:]))
+    dev = _collective_device(z, group, device)
+    if hi > lo:
+        local = sample_local(z[lo:hi], y[lo:hi]).to(dev)
+    else:
+        local = torch.empty((0,) + tuple(z.shape[1:]), dtype=torch.float32, device=dev)
     if not gather:
         return local
     sizes = [shard_range(n, r, world) for r in range(world)]

@@ -18,13 +18,16 @@ LIB_PATH = os.environ.get("VAVAE_B200_LIB") or os.path.join(_HERE, "libvavae_b20
 
 PREC_BF16, PREC_FP32 = 0, 1
 ODE_EULER, ODE_HEUN = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
+SAMPLE_SKIP_DISCARDED = 1
+EPI_QKV, EPI_SWIGLU, EPI_GATED_RESIDUAL = 0, 1, 2
 
 EXPORTS = [
     "vavae_abi_version", "vavae_last_error", "vavae_create", "vavae_destroy", "vavae_load_weight", "vavae_finalize",
     "vavae_forward", "vavae_forward_with_cfg", "vavae_sample_ode", "vavae_sample_ode_host", "vavae_launch_count",
     "vavae_device_bytes", "vavae_test_gemm_bf16", "vavae_test_attention_bf16", "vavae_time_kernel",
     "vavae_profile_begin", "vavae_profile_end", "vavae_set_gemm_two_cta", "vavae_sample_dopri5",
+    "vavae_device_status", "vavae_forward_rows", "vavae_test_gemm_epilogue", "vavae_sde_update",
     "vavae_decoder_create", "vavae_decoder_destroy", "vavae_decoder_load_weight", "vavae_decoder_finalize",
     "vavae_decoder_decode", "vavae_decoder_launch_count", "vavae_decoder_device_bytes",
 ]
@@ -38,6 +41,27 @@ class VavaeConfig(ctypes.Structure):
 
 
 _lib = None
+
+
+class VavaeEpilogueTest(ctypes.Structure):
+    """vavae_epilogue_test_t (include/vavae_b200.h)."""
+    _fields_ = [("kind", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("T", ctypes.c_int32), ("A", ctypes.c_void_p), ("W", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+                ("in_part", ctypes.c_void_p), ("in_nparts", ctypes.c_int32), ("in_dim", ctypes.c_int32),
+                ("sp", ctypes.c_void_p), ("sp_ld", ctypes.c_int32), ("H", ctypes.c_int32), ("hd", ctypes.c_int32),
+                ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p), ("qn_w", ctypes.c_void_p), ("kn_w", ctypes.c_void_p),
+                ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("vt", ctypes.c_void_p), ("out_bf16", ctypes.c_void_p),
+                ("ldo", ctypes.c_int32), ("X", ctypes.c_void_p), ("mod", ctypes.c_void_p), ("mod_ld", ctypes.c_int32),
+                ("gate_off", ctypes.c_int32), ("nx_w", ctypes.c_void_p), ("nx_scale_off", ctypes.c_int32),
+                ("nx_A", ctypes.c_void_p), ("nx_part", ctypes.c_void_p), ("nparts_out", ctypes.c_int32)]
+
+
+class VavaeSdeUpdate(ctypes.Structure):
+    """vavae_sde_update_t (include/vavae_b200.h)."""
+    _fields_ = [("mode", ctypes.c_int32), ("x", ctypes.c_void_p), ("v", ctypes.c_void_p), ("w", ctypes.c_void_p),
+                ("k1", ctypes.c_void_p), ("xh", ctypes.c_void_p), ("out", ctypes.c_void_p), ("out2", ctypes.c_void_p),
+                ("n", ctypes.c_int64)] + [(n, ctypes.c_float) for n in (
+                    "t", "dt", "diffusion", "var", "sqrt_2diffusion", "sqrt_dt", "c0", "c1")]
 
 
 class VavaeDecoderConfig(ctypes.Structure):
@@ -68,9 +92,14 @@ def load_library() -> ctypes.CDLL:
     lib.vavae_forward_with_cfg.argtypes = [c_void, c_void, c_void, c_void, c_float, c_int, c_float, c_int, c_void, c_int,
                                            c_void]
     lib.vavae_sample_ode.argtypes = [c_void, c_void, c_void, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float,
-                                     c_int, c_float, c_int, c_void, c_void, c_int, c_void]
+                                     c_int, c_float, c_int, c_void, c_void, c_int, c_int, c_void]
     lib.vavae_sample_ode_host.argtypes = [c_void, c_void, c_void, ctypes.POINTER(c_float), c_int, c_int, c_int, c_float,
-                                          c_int, c_float, c_int, c_void, c_int, c_void]
+                                          c_int, c_float, c_int, c_void, c_int, c_int, c_void]
+    lib.vavae_device_status.argtypes = [c_void, c_void]
+    lib.vavae_forward_rows.argtypes = [c_void]
+    lib.vavae_forward_rows.restype = ctypes.c_uint64
+    lib.vavae_test_gemm_epilogue.argtypes = [ctypes.POINTER(VavaeEpilogueTest), c_void]
+    lib.vavae_sde_update.argtypes = [ctypes.POINTER(VavaeSdeUpdate), c_void]
     lib.vavae_sample_dopri5.argtypes = [c_void, c_void, c_void, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                         ctypes.c_double, c_int, c_float, c_int, c_float, c_int, c_void, c_int,
                                         ctypes.POINTER(ctypes.c_int64), c_void]
@@ -166,13 +195,38 @@ class Engine:
         except Exception:
             pass
 
+    def _labels(self, y: torch.Tensor, batch: int) -> torch.Tensor:
+        """Labels as a contiguous int64 device tensor of shape (batch,).  A host tensor is range-checked here with
+        nn.Embedding's error (models/lightningdit.py:168); a device tensor is checked by the kernels themselves
+        (clamped read + device flag, raised by check_device_status / the *_host entry points) so that no
+        synchronisation is added to the call."""
+        if y.dim() != 1 or y.shape[0] != batch:
+            raise ValueError(f"y must have shape ({batch},), got {tuple(y.shape)}")
+        if torch.is_floating_point(y) or y.dtype == torch.bool:
+            raise RuntimeError("Expected tensor for argument #1 'indices' to have one of the following scalar types: "
+                               "Long, Int")
+        if not y.is_cuda and y.numel():
+            lo, hi = int(y.min()), int(y.max())
+            if lo < 0 or hi >= int(self.config["label_rows"]):
+                raise IndexError("index out of range in self")
+        return y.to(device=self.device, dtype=torch.int64).contiguous()
+
+    def check_device_status(self):
+        """Synchronises the current stream and raises IndexError if a kernel saw a label outside the embedding table
+        since the last check (nn.Embedding raises at once; a device-resident y cannot be checked without a sync)."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.vavae_device_status(self._h, ctypes.c_void_p(_stream(self.device)))
+        if rc != 0:
+            msg = self._lib.vavae_last_error().decode()
+            raise IndexError(msg) if "index out of range" in msg else RuntimeError("vavae_b200: " + msg)
+
     # -- LightningDiT.forward (models/lightningdit.py:391-418)
     def forward(self, x: torch.Tensor, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         x, t = _f32(x, self.device), _f32(t, self.device)
-        y = y.to(device=self.device, dtype=torch.int64).contiguous()
         self._check_x(x)
-        if t.shape != (x.shape[0],) or y.shape != (x.shape[0],):
-            raise ValueError("t and y must have shape (N,)")
+        if t.shape != (x.shape[0],):
+            raise ValueError(f"t must have shape ({x.shape[0]},), got {tuple(t.shape)}")
+        y = self._labels(y, x.shape[0])
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
             _check(self._lib.vavae_forward(self._h, x.data_ptr(), t.data_ptr(), y.data_ptr(), out.data_ptr(),
@@ -182,10 +236,12 @@ class Engine:
     # -- LightningDiT.forward_with_cfg (models/lightningdit.py:420-442)
     def forward_with_cfg(self, x, t, y, cfg_scale, cfg_interval=None, cfg_interval_start=None, cfg_channels=3):
         x, t = _f32(x, self.device), _f32(t, self.device)
-        y = y.to(device=self.device, dtype=torch.int64).contiguous()
         self._check_x(x)
         if x.shape[0] % 2:
             raise ValueError("forward_with_cfg expects 2n rows (conditional rows then null-label rows)")
+        if t.shape != (x.shape[0],):
+            raise ValueError(f"t must have shape ({x.shape[0]},), got {tuple(t.shape)}")
+        y = self._labels(y, x.shape[0])
         interval = 1 if cfg_interval is True else 0
         start = float(cfg_interval_start) if (interval and cfg_interval_start is not None) else 0.0
         if interval and cfg_interval_start is None:
@@ -199,10 +255,15 @@ class Engine:
 
     # -- ode.sample over a fixed grid (transport/integrators.py:107-126)
     def sample_ode(self, z, y, t_grid, method="euler", use_cfg=True, cfg_scale=1.0, cfg_interval=None,
-                   cfg_interval_start=None, cfg_channels=3, return_trace=False):
+                   cfg_interval_start=None, cfg_channels=3, return_trace=False, skip_discarded=False):
+        """skip_discarded: with the CFG-interval gate, do not run the unconditional forward of evaluations at
+        t < cfg_interval_start (its output is discarded, models/lightningdit.py:436-439).  Rows [0, n) of the result
+        are bit-identical to the literal mode; rows [n, 2n) are not the reference's (include/vavae_b200.h)."""
         z = _f32(z, self.device)
-        y = y.to(device=self.device, dtype=torch.int64).contiguous()
         self._check_x(z)
+        if use_cfg and z.shape[0] % 2:
+            raise ValueError("CFG sampling expects 2n rows (conditional rows then null-label rows)")
+        y = self._labels(y, z.shape[0])
         grid = torch.as_tensor(t_grid, dtype=torch.float32).cpu().contiguous()
         meth = {"euler": ODE_EULER, "heun": ODE_HEUN, "heun2": ODE_HEUN}[method]
         n_evals = (len(grid) - 1) * (2 if meth == ODE_HEUN else 1)
@@ -215,15 +276,17 @@ class Engine:
             _check(self._lib.vavae_sample_ode(
                 self._h, z.data_ptr(), y.data_ptr(), gptr, len(grid), meth, 1 if use_cfg else 0, float(cfg_scale),
                 interval, start, int(cfg_channels), out.data_ptr(), trace.data_ptr() if return_trace else None,
-                z.shape[0], ctypes.c_void_p(_stream(self.device))))
+                z.shape[0], SAMPLE_SKIP_DISCARDED if skip_discarded else 0, ctypes.c_void_p(_stream(self.device))))
         return (out, trace) if return_trace else out
 
     # -- adaptive dopri5 (torchdiffeq.odeint(method="dopri5") as reached from transport/integrators.py:118-125)
     def sample_dopri5(self, z, y, t0=0.0, t1=1.0, atol=1e-6, rtol=1e-3, use_cfg=True, cfg_scale=1.0, cfg_interval=None,
                       cfg_interval_start=None, cfg_channels=3, return_stats=False):
         z = _f32(z, self.device)
-        y = y.to(device=self.device, dtype=torch.int64).contiguous()
         self._check_x(z)
+        if use_cfg and z.shape[0] % 2:
+            raise ValueError("CFG sampling expects 2n rows (conditional rows then null-label rows)")
+        y = self._labels(y, z.shape[0])
         out = torch.empty_like(z)
         interval = 1 if cfg_interval is True else 0
         start = float(cfg_interval_start) if (interval and cfg_interval_start is not None) else 0.0
@@ -238,11 +301,14 @@ class Engine:
         return out
 
     def sample_ode_host(self, z_host, y_host, t_grid, out_host, method="euler", use_cfg=True, cfg_scale=1.0,
-                        cfg_interval=None, cfg_interval_start=None, cfg_channels=3):
+                        cfg_interval=None, cfg_interval_start=None, cfg_channels=3, skip_discarded=False):
         """End-to-end entry: HOST (ideally pinned) buffers in and out; H2D/D2H inside the call."""
         assert z_host.dtype == torch.float32 and not z_host.is_cuda and z_host.is_contiguous()
         assert y_host.dtype == torch.int64 and not y_host.is_cuda and y_host.is_contiguous()
         assert out_host.dtype == torch.float32 and not out_host.is_cuda and out_host.shape == z_host.shape
+        self._check_x(z_host)
+        if y_host.shape != (z_host.shape[0],):
+            raise ValueError(f"y must have shape ({z_host.shape[0]},), got {tuple(y_host.shape)}")
         grid = torch.as_tensor(t_grid, dtype=torch.float32).cpu().contiguous()
         meth = {"euler": ODE_EULER, "heun": ODE_HEUN, "heun2": ODE_HEUN}[method]
         interval = 1 if cfg_interval is True else 0
@@ -252,7 +318,7 @@ class Engine:
             _check(self._lib.vavae_sample_ode_host(
                 self._h, z_host.data_ptr(), y_host.data_ptr(), gptr, len(grid), meth, 1 if use_cfg else 0,
                 float(cfg_scale), interval, start, int(cfg_channels), out_host.data_ptr(), z_host.shape[0],
-                ctypes.c_void_p(_stream(self.device))))
+                SAMPLE_SKIP_DISCARDED if skip_discarded else 0, ctypes.c_void_p(_stream(self.device))))
         return out_host
 
     def time_kernel(self, kernel: str, rows: int, iters: int = 10):
@@ -276,6 +342,11 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.vavae_launch_count(self._h))
+
+    @property
+    def forward_rows(self) -> int:
+        """Model rows pushed through the layer stack since creation (forwards actually executed)."""
+        return int(self._lib.vavae_forward_rows(self._h))
 
     @property
     def device_bytes(self) -> int:
@@ -315,4 +386,40 @@ def test_attention_bf16(q, k, vt, hd: int) -> torch.Tensor:
     with torch.cuda.device(q.device):
         _check(lib.vavae_test_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), B, H, T, hd,
                                              ctypes.c_void_p(_stream(q.device))))
+    return out
+
+
+def test_gemm_epilogue(**fields) -> int:
+    """One launch of the production tcgen05 GEMM with a fused epilogue on caller-provided CUDA tensors
+    (vavae_test_gemm_epilogue).  Tensor-valued fields are passed as torch tensors; returns nparts_out."""
+    lib = load_library()
+    t = VavaeEpilogueTest()
+    dev = None
+    keep = []
+    for k, v in fields.items():
+        if isinstance(v, torch.Tensor):
+            assert v.is_cuda and v.is_contiguous(), k
+            dev = v.device
+            keep.append(v)
+            setattr(t, k, v.data_ptr())
+        else:
+            setattr(t, k, int(v))
+    with torch.cuda.device(dev):
+        _check(lib.vavae_test_gemm_epilogue(ctypes.byref(t), ctypes.c_void_p(_stream(dev))))
+    return int(t.nparts_out)
+
+
+def sde_update(mode: int, x: torch.Tensor, out: torch.Tensor, v=None, w=None, k1=None, xh=None, out2=None, **scalars):
+    """One fused pass of the SDE sampler's elementwise update (vavae_sde_update; modes in include/vavae_b200.h)."""
+    lib = load_library()
+    u = VavaeSdeUpdate(mode=int(mode), n=x.numel())
+    for name, ten in (("x", x), ("v", v), ("w", w), ("k1", k1), ("xh", xh), ("out", out), ("out2", out2)):
+        if ten is not None:
+            if not (ten.is_cuda and ten.is_contiguous() and ten.dtype == torch.float32 and ten.numel() == x.numel()):
+                raise ValueError(f"sde_update: {name} must be a contiguous fp32 CUDA tensor of x's size")
+            setattr(u, name, ten.data_ptr())
+    for k, val in scalars.items():
+        setattr(u, k, float(val))
+    with torch.cuda.device(x.device):
+        _check(lib.vavae_sde_update(ctypes.byref(u), ctypes.c_void_p(_stream(x.device))))
     return out

@@ -187,8 +187,29 @@ class LightningDiT(nn.Module):
 
     def _weights_key(self):
         dev = self.pos_embed.device
-        return (str(dev), self.precision, tuple(p._version for p in self.parameters()),
-                tuple(p.data_ptr() for p in self.parameters()))
+        tensors = self.__dict__.get("_key_tensors")
+        if tensors is None:   # the module tree is fixed after __init__: walk it once, not on every forward call
+            tensors = list(self.parameters()) + list(self.buffers())   # buffers: feat_rope.freqs_cos / freqs_sin
+            self.__dict__["_key_tensors"] = tensors
+        return (str(dev), self.precision, tuple(p._version for p in tensors), tuple(p.data_ptr() for p in tensors))
+
+    def invalidate_engine(self):
+        """Forces the next call to re-upload the weights.  The engine holds its own packed COPY of the parameters;
+        load_state_dict(), .to()/.cuda()/.float() and in-place ops that bump the autograd version counter are
+        detected automatically, but writes through `.data` (EMA-style `p.data.mul_(..)`, `p.data.copy_(..)`) are
+        invisible to PyTorch's version counter - call this after such an update."""
+        self._engine_key = None
+
+    refresh_weights = invalidate_engine
+
+    def _apply(self, fn, *args, **kwargs):                          # .to() / .cuda() / .float() / .half()
+        self._engine_key = None
+        self.__dict__.pop("_key_tensors", None)                     # _apply may replace Parameter objects
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._engine_key = None
+        return super().load_state_dict(*args, **kwargs)
 
     def engine(self) -> Engine:
         """Builds (or rebuilds after a weight / device change) the CUDA engine for this module."""

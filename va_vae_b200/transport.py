@@ -3,7 +3,8 @@
 Reference: /root/reference/LightningDiT/transport/__init__.py:3-72 (create_transport),
 transport/transport.py:40-111,218-250,270-283,398-443 (Transport.check_interval / get_drift, Sampler.sample_ode),
 transport/integrators.py:77-126 (class ode), plus Sampler.sample_sde (transport.py:336-396, integrators.py:8-75) for the
-linear path.  Training losses and likelihoods are out of scope for this engine.
+linear path, and the forward-only value of Transport.training_losses (transport.py:112-215, path.py:18-136) for the
+linear path with a velocity model.  Likelihoods are out of scope for this engine.
 
 `sample_fn = Sampler(transport).sample_ode(...)` returns a bound `ode.sample` exactly like the reference; when
 `sample_fn(x, model.forward_with_cfg, **kw)` (or `model.forward`) is called with a bound method of the B200
@@ -14,6 +15,7 @@ generic fixed-grid loop that only calls `model(x, t, **kw)`.
 from __future__ import annotations
 
 import enum
+import os
 
 import numpy as np
 import torch as th
@@ -80,8 +82,73 @@ class Transport:
         body_fn.is_plain_velocity = True
         return body_fn
 
-    def training_losses(self, *a, **k):
-        raise NotImplementedError("training is out of scope for the B200 sampling engine")
+    # ---- training-side reuse of the forward: loss VALUES only, no autograd through the engine
+    def sample_logit_normal(self, mu, sigma, size=1):
+        """transport/transport.py:112-122 (scipy's norm.rvs on numpy's global RNG, logistic, fp32 tensor)."""
+        from scipy.stats import norm
+        samples = norm.rvs(loc=mu, scale=sigma, size=size)
+        samples = 1 / (1 + np.exp(-samples))
+        return th.tensor(samples, dtype=th.float32)
+
+    def sample_in_range(self, mu, sigma, target_size, range_min=0, range_max=0.5):
+        """transport/transport.py:124-133."""
+        samples = []
+        while len(samples) < target_size:
+            generated = self.sample_logit_normal(mu, sigma, size=target_size)
+            samples.extend(generated[(generated >= range_min) & (generated <= range_max)])
+        return th.tensor(samples[:target_size])
+
+    def sample(self, x1, sp_timesteps=None, shifted_mu=0):
+        """transport/transport.py:135-166: x0 ~ N(0, I) like x1; t uniform / logit-normal / partial range.  Same RNG
+        calls in the same order as the reference, so a seeded run draws the same (t, x0)."""
+        x0 = th.randn_like(x1)
+        t0, t1 = self.check_interval(self.train_eps, self.sample_eps)
+        if not self.use_lognorm:
+            if self.partitial_train is not None and th.rand(1) < self.partial_ratio:
+                t = th.rand((x1.shape[0],)) * (self.partitial_train[1] - self.partitial_train[0]) + self.partitial_train[0]
+            else:
+                t = th.rand((x1.shape[0],)) * (t1 - t0) + t0
+        elif not self.shift_lg:
+            if self.partitial_train is not None and th.rand(1) < self.partial_ratio:
+                t = self.sample_in_range(0, 1, x1.shape[0], range_min=self.partitial_train[0],
+                                         range_max=self.partitial_train[1])
+            else:
+                t = self.sample_logit_normal(0, 1, size=x1.shape[0]) * (t1 - t0) + t0
+        else:
+            assert self.partitial_train is None, "Shifted lognormal distribution is not compatible with partial training"
+            t = self.sample_logit_normal(shifted_mu, 1, size=x1.shape[0]) * (t1 - t0) + t0
+        if sp_timesteps is not None:
+            t = th.rand((x1.shape[0],)) * (sp_timesteps[1] - sp_timesteps[0]) + sp_timesteps[0]
+        return t.to(x1), x0, x1
+
+    @staticmethod
+    def plan(t, x0, x1):
+        """ICPlan.plan (transport/path.py:114-136): xt = t*x1 + (1-t)*x0 ; ut = 1*x1 + (-1)*x0."""
+        te = t.view(t.size(0), *([1] * (x1.dim() - 1)))
+        xt = te * x1 + (1 - te) * x0
+        ut = 1 * x1 + -1 * x0
+        return t, xt, ut
+
+    @th.no_grad()
+    def training_losses(self, model, x1, model_kwargs=None, sp_timesteps=None, shifted_mu=0):
+        """transport/transport.py:169-215 for path_type='Linear', prediction='velocity' (every reference config):
+        returns {'pred', 'loss' [, 'cos_loss']} with the reference's values.  FORWARD ONLY: `model` is evaluated by the
+        inference engine, nothing is differentiable - this serves validation-loss curves and parity checks of the
+        training objective, not an optimiser step (the backward pass is out of scope)."""
+        if self.path_type != PathType.LINEAR or self.model_type != ModelType.VELOCITY:
+            raise NotImplementedError("training_losses covers path_type='Linear' with prediction='velocity'")
+        if model_kwargs is None:
+            model_kwargs = {}
+        t, x0, x1 = self.sample(x1, sp_timesteps, shifted_mu)
+        t, xt, ut = self.plan(t, x0, x1)
+        model_output = model(xt, t, **model_kwargs)
+        B, *_, C = xt.shape
+        assert model_output.size() == (B, *xt.size()[1:-1], C)
+        mean_flat = lambda v: th.mean(v, dim=list(range(1, v.dim())))       # transport/utils.py:13-17
+        terms = {"pred": model_output, "loss": mean_flat((model_output - ut) ** 2)}
+        if self.use_cosine_loss:
+            terms["cos_loss"] = mean_flat(1 - th.nn.functional.cosine_similarity(model_output, ut, dim=1))
+        return terms
 
 
 def create_transport(path_type="Linear", prediction="velocity", loss_weight=None, train_eps=None, sample_eps=None,
@@ -135,7 +202,7 @@ class ode:
     """transport/integrators.py:77-126."""
 
     def __init__(self, drift, *, t0, t1, sampler_type, num_steps, atol, rtol, timestep_shift, keep_trajectory=False,
-                 native_ok=True):
+                 native_ok=True, skip_discarded_uncond=False):
         assert t0 < t1, "ODE sampler has to be in forward time"
         self.drift = drift
         self.t = _time_grid(t0, t1, num_steps, timestep_shift)
@@ -143,6 +210,7 @@ class ode:
         self.sampler_type = sampler_type
         self.keep_trajectory = keep_trajectory
         self.native_ok = native_ok
+        self.skip_discarded_uncond = skip_discarded_uncond
 
     def _native_target(self, model):
         from .lightningdit import LightningDiT
@@ -176,7 +244,8 @@ class ode:
             owner._require_eval()
             if name == "forward_with_cfg":
                 final = eng.sample_ode(x, model_kwargs["y"], self.t, method, True, model_kwargs["cfg_scale"],
-                                       model_kwargs.get("cfg_interval"), model_kwargs.get("cfg_interval_start"), 3)
+                                       model_kwargs.get("cfg_interval"), model_kwargs.get("cfg_interval_start"), 3,
+                                       skip_discarded=self.skip_discarded_uncond)
             else:
                 final = eng.sample_ode(x, model_kwargs["y"], self.t, method, False)
             return LazyTrajectory(final, len(self.t))
@@ -269,7 +338,12 @@ class Sampler:
         self.drift = self.transport.get_drift()
 
     def sample_ode(self, *, sampling_method="dopri5", num_steps=50, atol=1e-6, rtol=1e-3, reverse=False,
-                   timestep_shift=0.0, keep_trajectory=False):
+                   timestep_shift=0.0, keep_trajectory=False, skip_discarded_uncond=False):
+        """Reference arguments (transport.py:398-408) plus two keyword-only extensions that default to the reference's
+        behaviour: keep_trajectory (materialise every grid point) and skip_discarded_uncond - with
+        `cfg_interval=True`, do not run the unconditional forward of evaluations at t < cfg_interval_start, whose
+        output forward_with_cfg throws away (lightningdit.py:436-439).  Callers keep `[-1].chunk(2)[0]`
+        (inference.py:216-218); those rows are bit-identical with and without the option, the other half is not."""
         native_ok = not reverse
         if reverse:
             def drift(x, t, model, **kwargs):
@@ -279,7 +353,8 @@ class Sampler:
         t0, t1 = self.transport.check_interval(self.transport.train_eps, self.transport.sample_eps, sde=False, eval=True,
                                                reverse=reverse, last_step_size=0.0)
         _ode = ode(drift=drift, t0=t0, t1=t1, sampler_type=sampling_method, num_steps=num_steps, atol=atol, rtol=rtol,
-                   timestep_shift=timestep_shift, keep_trajectory=keep_trajectory, native_ok=native_ok)
+                   timestep_shift=timestep_shift, keep_trajectory=keep_trajectory, native_ok=native_ok,
+                   skip_discarded_uncond=skip_discarded_uncond)
         return _ode.sample
 
     def sample_sde(self, *, sampling_method="Euler", diffusion_form="SBDM", diffusion_norm=1.0, last_step="Mean",
@@ -290,7 +365,9 @@ class Sampler:
         does), same list of ``num_steps`` states as return value.  The reference evaluates the model twice per drift
         (once for the velocity, once for the score, transport.py:306-308); both are derived here from ONE evaluation,
         which is bit-identical for a deterministic model and halves the cost.  Every model evaluation is a native
-        forward when ``model`` is a bound method of the B200 module; the elementwise update runs in PyTorch."""
+        forward when ``model`` is a bound method of the B200 module, and for CUDA states the whole elementwise update of
+        a step (drift, score, Euler-Maruyama / Heun stage) is ONE pass of the library's `vavae_sde_update` kernel with
+        the reference's fp32 operation order (coefficients are host scalars because the batch shares one time)."""
         if self.transport.path_type != PathType.LINEAR or self.transport.model_type != ModelType.VELOCITY:
             raise NotImplementedError("sample_sde covers path_type='Linear' with prediction='velocity'")
         if sampling_method not in ("Euler", "Heun"):
@@ -357,11 +434,58 @@ class Sampler:
             k2 = sde_drift(xp, t_cur + dt, model, **kw)
             return xhat + 0.5 * dt * (k1 + k2)
 
-        step = em_step if sampling_method == "Euler" else heun_step
+        # ---- native fused update (CUDA states): same arithmetic, one kernel per stage instead of ~10 tensor ops
+        from . import engine as _eng
+
+        def coeffs(ti, device):
+            """fp32 scalars of a step, computed with the same torch ops, on the same device, as the tensor path
+            applies elementwise (cos / sin of the 'decreasing' forms may differ in the last bit between CPU and GPU)."""
+            t = th.ones(1, device=device) * ti
+            diffusion = diffusion_fn(t.view(1, 1), t)
+            diffusion = diffusion if th.is_tensor(diffusion) else th.tensor(float(diffusion))
+            sigma_t = 1 - t
+            var = sigma_t ** 2 - (t / 1) * (-1) * sigma_t
+            return dict(t=float(t), diffusion=float(diffusion), var=float(var),
+                        sqrt_2diffusion=float(th.sqrt(2 * diffusion)), sqrt_dt=float(th.sqrt(dt)))
+
+        def native(x):   # VAVAE_SDE_TENSOR_OPS=1: developer knob, keeps the tensor-op path on the GPU (A/B in the tests)
+            return x.is_cuda and x.dtype == th.float32 and os.environ.get("VAVAE_SDE_TENSOR_OPS") != "1"
+
+        def em_step_native(x, ti, model, **kw):
+            w_cur = th.randn(x.size()).to(x)                                  # same RNG stream as the reference
+            t = th.ones(x.size(0)).to(x) * ti
+            v = velocity(x, t, model, **kw)
+            return _eng.sde_update(0, x.contiguous(), th.empty_like(x), v=v.contiguous(), w=w_cur, dt=float(dt), **coeffs(ti, x.device))
+
+        def heun_step_native(x, ti, model, **kw):
+            w_cur = th.randn(x.size()).to(x)
+            t_cur = th.ones(x.size(0)).to(x) * ti
+            c0, c1 = coeffs(ti, x.device), coeffs(float(th.ones(1) * ti + dt), x.device)
+            xhat = _eng.sde_update(1, x.contiguous(), th.empty_like(x), w=w_cur, dt=float(dt), **c0)
+            v1 = velocity(xhat, t_cur, model, **kw)
+            k1 = th.empty_like(x)
+            xp = _eng.sde_update(2, xhat, th.empty_like(x), v=v1.contiguous(), out2=k1, dt=float(dt), **c0)
+            v2 = velocity(xp, t_cur + dt, model, **kw)
+            return _eng.sde_update(3, xp, th.empty_like(x), v=v2.contiguous(), k1=k1, xh=xhat, dt=float(dt), **c1)
+
+        def step(x, ti, model, **kw):
+            if native(x):
+                return (em_step_native if sampling_method == "Euler" else heun_step_native)(x, ti, model, **kw)
+            return (em_step if sampling_method == "Euler" else heun_step)(x, ti, model, **kw)
 
         def last_step_fn(x, t, model, **kw):                                  # transport.py:313-334
             if last_step is None:
                 return x
+            if native(x):
+                c = coeffs(t1, x.device)
+                v = velocity(x, t, model, **kw).contiguous()
+                if last_step == "Mean":
+                    return _eng.sde_update(4, x.contiguous(), th.empty_like(x), v=v, dt=float(last_step_size), **c)
+                if last_step == "Tweedie":
+                    alpha, sigma = t[0], 1 - t[0]
+                    return _eng.sde_update(5, x.contiguous(), th.empty_like(x), v=v, dt=0.0, c0=float(alpha),
+                                           c1=float((sigma ** 2) / alpha), **c)
+                return _eng.sde_update(6, x.contiguous(), th.empty_like(x), v=v, dt=float(last_step_size), **c)
             if last_step == "Mean":
                 return x + sde_drift(x, t, model, **kw) * last_step_size
             if last_step == "Tweedie":
