@@ -6,7 +6,10 @@ sys.path.insert(0, ROOT)
 import torch
 import va_vae_b200 as V
 from oracle import lightningdit_oracle as O
-for name, rows in (("LightningDiT-B/1", 512), ("LightningDiT-XL/1", 256)):
+CASES = (("LightningDiT-B/1", 512), ("LightningDiT-XL/1", 256))
+if os.environ.get("AB_MODELS") == "xl":
+    CASES = CASES[1:]
+for name, rows in CASES:
     cfg = O.config_from_name(name, input_size=16, num_classes=1000)
     cfg.depth = 1
     sd = O.init_state_dict(cfg, seed=0)

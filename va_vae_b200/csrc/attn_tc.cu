@@ -19,6 +19,7 @@
 #include "tc_ptx.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace vv {
 
@@ -278,6 +279,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           ptx::tmem_ld_x32(trow, ra);
           tmem_ld_wait_dep32(ra);
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (a.experiment == 1) m4[0] = 0.f;   // EXPERIMENT (timing only): no row-max pass, offset 0
+          if (a.experiment != 1) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             uint32_t* cur = (i & 1) ? rb : ra;
@@ -291,6 +294,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               m4[3] = fmaxf(m4[3], __uint_as_float(cur[j + 3]));
             }
             tmem_ld_wait_dep32(nxt);
+          }
           }
           const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           m_new = fmaxf(m_run, mx);
@@ -536,6 +540,12 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   const int per_sm = smem <= 113 * 1024 ? 2 : 1;
   const int grid = std::min(n_items, sms * per_sm);
   const bool multi = a.T > AT_BKV;
+  TcAttnArgs aa = a;
+  {
+    static int exp_mode = -1;
+    if (exp_mode < 0) { const char* e = std::getenv("VAVAE_ATTN_EXPERIMENT"); exp_mode = e ? std::atoi(e) : 0; }
+    aa.experiment = exp_mode;
+  }
   static std::atomic<uint64_t> attr_devices{0};   // per device; not a stream operation, safe during graph capture
   if (!device_marked(attr_devices)) {
     VV_CUDA(cudaFuncSetAttribute(k_attention_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -557,9 +567,9 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (multi && a.hd + 1 <= 80) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<80>, tmQ, tmK, tmV, tmQt, tmKt, a));
-  else if (multi) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<128>, tmQ, tmK, tmV, tmQt, tmKt, a));
-  else VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<0>, tmQ, tmK, tmV, tmQt, tmKt, a));
+  if (multi && a.hd + 1 <= 80) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<80>, tmQ, tmK, tmV, tmQt, tmKt, aa));
+  else if (multi) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<128>, tmQ, tmK, tmV, tmQt, tmKt, aa));
+  else VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<0>, tmQ, tmK, tmV, tmQt, tmKt, aa));
   VV_LAUNCH_CHECK();
 }
 

@@ -1383,6 +1383,9 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
   std::function<void()> fn;
   const float* rcos = c.use_rope ? e->W("feat_rope.freqs_cos").d : nullptr;
   const float* rsin = c.use_rope ? e->W("feat_rope.freqs_sin").d : nullptr;
+  // the kernels are timed as the sampler launches them: with the fused RMSNorm producer / consumer sides when active
+  const bool fused = e->fuse;
+  const float* sp0 = (fused && !c.wo_shift) ? e->mod + e->NM : nullptr;
   if (k == "gemm_qkv") {
     *work = 2.0 * M * 3.0 * D * D;
     fn = [&] {
@@ -1390,6 +1393,11 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
       a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.qk_rms = c.use_rmsnorm; a.H = H;
       a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
       if (c.use_qknorm) { a.qn_w = e->W(blk(0, "attn.q_norm.weight")).d; a.kn_w = e->W(blk(0, "attn.k_norm.weight")).d; }
+      if (fused) {   // as launched for layers >= 1: 1/rms from the previous w3's partial sums, per-sample sp vector
+        TcGemmArgs w3 = tc_args(e->Hh_h, e->Spad, e->lw[0].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL, nullptr);
+        a.in_part = e->part2; a.in_nparts = 2 * cdiv(D, gemm_tc_pick_bn(w3)); a.in_dim = D;
+        a.sp = sp0 ? sp0 : a.bias; a.sp_ld = sp0 ? e->NMx : 0;
+      }
       launch_gemm_tc(a, s);
     };
   } else if (k == "gemm_proj") {
@@ -1397,6 +1405,7 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     fn = [&] {
       TcGemmArgs pr = tc_args(e->O_h, D, e->lw[0].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(0, "attn.proj.bias")).d);
       pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NMx; pr.gate_off = mo.gate_msa; pr.T = T;
+      if (fused) { pr.nx_w = e->W(blk(0, "norm2.weight")).d; pr.nx_scale_off = mo.scale_mlp; pr.nx_A = e->A_h; pr.nx_part = e->part1; }
       launch_gemm_tc(pr, s);
     };
   } else if (k == "gemm_w12") {
@@ -1404,7 +1413,12 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     *work = 2.0 * M * 2.0 * S * D;
     fn = [&] {
       TcGemmArgs a = tc_args(e->A_h, D, e->lw[0].w1, D, M, ((2 * S + 3) / 4) * 4, D, TC_EPI_SWIGLU, e->lw[0].b1);
-      a.out = e->Hh_h; a.ldo = e->Spad;
+      a.out = e->Hh_h; a.ldo = e->Spad; a.T = T;
+      if (fused) {
+        TcGemmArgs pr = tc_args(e->O_h, D, e->lw[0].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, nullptr);
+        a.in_part = e->part1; a.in_nparts = 2 * cdiv(D, gemm_tc_pick_bn(pr)); a.in_dim = D;
+        a.sp = sp0 ? sp0 + 3 * D : a.bias; a.sp_ld = sp0 ? e->NMx : 0;
+      }
       launch_gemm_tc(a, s);
     };
   } else if (k == "gemm_w3") {
@@ -1413,6 +1427,7 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
       TcGemmArgs a = tc_args(e->Hh_h, e->Spad, e->lw[0].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL,
                              e->W(blk(0, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d);
       a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NMx; a.gate_off = mo.gate_mlp; a.T = T;
+      if (fused) { a.nx_w = e->W(blk(0, "norm1.weight")).d; a.nx_scale_off = mo.scale_msa; a.nx_A = e->A_h; a.nx_part = e->part2; }
       launch_gemm_tc(a, s);
     };
   } else if (k == "attention") {

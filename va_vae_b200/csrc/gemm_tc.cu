@@ -599,10 +599,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
 // rows of A and HALF of the W tile (BN/2 rows); the leader's single thread issues M=256 MMAs that read both CTAs'
 // shared memory and write each CTA's 128 x BN accumulator into its own TMEM.  Per flop this halves the W-tile
 // shared-memory fill and L2 traffic, which is what limits (and powers) the 1-CTA kernel.
+// Column tiles: n_tiles - 1 tiles of BN columns plus a last tile of BNlast <= BN columns (its own W tensor map, tmBl,
+// with a shorter box): N = 1152 runs as 4 x 256 + 128 and N = 3456 as 13 x 256 + 128 instead of 6 / 18 tiles of 192 -
+// the tensor core is fed 256-wide instructions wherever the problem allows it.
 template <int EPI, int CW, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmArgs a,
-          const int BN, const int nstages) {
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmBl, const TcGemmArgs a, const int BN, const int BNlast,
+          const int nstages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_rows = TWO ? BN / 2 : BN;                 // W-tile rows this CTA loads
@@ -623,6 +627,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmBl);
     for (int i = 0; i < nstages; ++i) {
       ptx::mbar_init(&bars->full[i], 1);
       ptx::mbar_init(&bars->empty[i], 1);
@@ -657,6 +662,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t phase = 0;
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const bool last_n = n_blk == n_tiles - 1 && BNlast != BN;   // narrower last column tile
+        const int bn_t = last_n ? BNlast : BN;
+        const int b_rows_t = TWO ? bn_t / 2 : bn_t;
+        const CUtensorMap* tmb = last_n ? &tmBl : &tmB;
         const int a_row0 = m_blk * tile_m + (int)rank * TC_BM;   // first A row (= output pixel) of this CTA's tile
         // implicit-GEMM convolution: the tile is 128 consecutive pixels of one image (a row segment when W >= 128,
         // 128 / W whole rows otherwise); tap (dy, dx) shifts the box, TMA zero-fills what falls outside the image
@@ -678,19 +687,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const int dy = a.conv_taps == 9 ? tap / 3 - 1 : 0, dx = a.conv_taps == 9 ? tap % 3 - 1 : 0;
           if (TWO) {
             // both CTAs' bytes are credited to the leader's barrier; only the leader arms it (with the pair's total)
-            if (rank == 0) ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * stage_bytes));
+            if (rank == 0) ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(2 * (TC_A_BYTES + b_rows_t * 128)));
             if (a.conv_taps)
               ptx2::tma_load_4d_2sm(sa, &tmA, &bars->full[stage], cb * TC_BK, cv_w + dx, cv_h + dy, cv_n);
             else
               ptx2::tma_load_2d_2sm(sa, &tmA, &bars->full[stage], kb * TC_BK, a_row0);
-            ptx2::tma_load_2d_2sm(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN + (int)rank * b_rows);
+            ptx2::tma_load_2d_2sm(sb, tmb, &bars->full[stage], kb * TC_BK, n_blk * BN + (int)rank * b_rows_t);
           } else {
-            ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
+            ptx::mbar_expect_tx(&bars->full[stage], (uint32_t)(TC_A_BYTES + b_rows_t * 128));
             if (a.conv_taps)
               ptx::tma_load_4d(sa, &tmA, &bars->full[stage], cb * TC_BK, cv_w + dx, cv_h + dy, cv_n);
             else
               ptx::tma_load_2d(sa, &tmA, &bars->full[stage], kb * TC_BK, a_row0);
-            ptx::tma_load_2d(sb, &tmB, &bars->full[stage], kb * TC_BK, n_blk * BN);
+            ptx::tma_load_2d(sb, tmb, &bars->full[stage], kb * TC_BK, n_blk * BN);
           }
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
@@ -699,12 +708,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(tile_m, BN);
+      const uint32_t idesc_main = ptx::make_idesc_bf16(tile_m, BN), idesc_last = ptx::make_idesc_bf16(tile_m, BNlast);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
+        const uint32_t idesc = (tile % n_tiles == n_tiles - 1) ? idesc_last : idesc_main;
         ptx::mbar_wait(&bars->tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)as * 256;
@@ -758,10 +768,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
-      if (CW == 32 && fast_ok && m0 + TC_BM <= a.M && n0 + BN <= a.N) {
+      const int bn_t = (n_blk == n_tiles - 1) ? BNlast : BN;   // columns of this tile
+      if (CW == 32 && fast_ok && (bn_t % 32 == 0) && m0 + TC_BM <= a.M && n0 + bn_t <= a.N) {
         // interior tile of a production epilogue: guard-free path
         epi_tile_fast<EPI>(a, ptx::smem_u32(st), tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256,
-                           &bars->tfull[as], aphase, m0, n0, n_blk, BN, q, half, lane);
+                           &bars->tfull[as], aphase, m0, n0, n_blk, bn_t, q, half, lane);
         release_acc(as);
         as ^= 1;
         if (as == 0) aphase ^= 1;
@@ -770,7 +781,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int wrow0 = m0 + q * 32;     // first row of this warp
       const int my_row = wrow0 + lane;   // thread == row domain
       const int wb = wrow0 / a.T, wt0 = wrow0 - wb * a.T;  // sample / first token of the warp (valid if rows_one_sample)
-      int n_chunks = (min(BN, a.N - n0) + CW - 1) / CW;
+      int n_chunks = (min(bn_t, a.N - n0) + CW - 1) / CW;
 
       // ---- prefetch for the gated-residual epilogue: the fp32 residual tile is loaded one chunk ahead so the
       //      HBM/L2 latency overlaps the TMEM drain of the previous chunk (and the wait for the MMA)
@@ -1146,7 +1157,37 @@ static bool want_two_cta(const TcGemmArgs& a) {
     default: return false;
   }
 }
+// VAVAE_GEMM_BN (developer knob for same-box A/B runs): unset = 256-wide tiles plus one narrower last tile where N is
+// not a multiple of 256 ("mixed"); "legacy" = one width per problem (256 / 192 / 128 by tile efficiency); a number
+// forces that width for the layer GEMMs.
+static int bn_mode() {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = std::getenv("VAVAE_GEMM_BN");
+    if (!e || !e[0]) mode = 0;
+    else if (e[0] == 'l') mode = -1;
+    else mode = std::atoi(e);
+  }
+  return mode;
+}
+static bool layer_gemm(const TcGemmArgs& a) {
+  if (a.conv_taps || a.gn_part) return false;
+  return a.epi == TC_EPI_GATED_RESIDUAL || a.epi == TC_EPI_SWIGLU || a.epi == TC_EPI_GELU_BF16 ||
+         (a.epi == TC_EPI_QKV && !a.qn_w && (a.H * a.hd) % 32 == 0);
+}
+// Width of the last column tile: the remainder when the problem is tiled 256-wide and the remainder is a whole number
+// of 32-column epilogue chunks; otherwise the main width (a partial last tile then relies on TMA zero fill).
+int gemm_tc_last_bn(const TcGemmArgs& a, int BN) {
+  const int rem = a.N % BN;
+  if (bn_mode() == 0 && layer_gemm(a) && BN == 256 && rem != 0 && rem % 32 == 0) return rem;
+  return BN;
+}
 int gemm_tc_pick_bn(const TcGemmArgs& a) {
+  if (layer_gemm(a)) {
+    const int mode = bn_mode();
+    if (mode > 0 && mode % 32 == 0 && mode <= 256) return mode;
+    if (mode == 0 && a.N > 256 && a.N % 256 != 0 && (a.N % 256) % 32 == 0) return 256;
+  }
   if (a.epi == TC_EPI_FINAL) {
     int bn = ((a.N + 15) / 16) * 16;
     VV_CHECK(bn <= 256, "final linear wider than 256 columns is not supported");
@@ -1183,6 +1224,7 @@ int get_gemm_two_cta() { return g_two_cta; }
 
 template <int EPI, int CW, bool TWO>
 static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
+  const int BNlast = gemm_tc_last_bn(a, BN);
   const int b_rows = TWO ? BN / 2 : BN;
   const int stage_bytes = TC_A_BYTES + b_rows * 128;
   const int fixed = 8 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024;
@@ -1206,6 +1248,9 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
     tmA = make_tmap_2d_bf16(a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, TC_BK, TC_BM);
   }
   CUtensorMap tmB = make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK, (uint32_t)b_rows);
+  CUtensorMap tmBl = BNlast == BN ? tmB
+                                  : make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK,
+                                                      (uint32_t)(TWO ? BNlast / 2 : BNlast));
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
@@ -1222,7 +1267,7 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
     cfg.gridDim = dim3(tiles < num_sms() ? tiles : num_sms());
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, false>, tmA, tmB, a, BN, nstages));
+    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, false>, tmA, tmB, tmBl, a, BN, BNlast, nstages));
   } else {
     const int tiles = cdiv(a.M, 2 * TC_BM) * cdiv(a.N, BN);
     const int pairs = std::min(tiles, num_sms() / 2);
@@ -1234,7 +1279,7 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
     ++na;
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, true>, tmA, tmB, a, BN, nstages));
+    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, true>, tmA, tmB, tmBl, a, BN, BNlast, nstages));
   }
   VV_LAUNCH_CHECK();
 }

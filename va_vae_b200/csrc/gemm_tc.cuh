@@ -81,6 +81,7 @@ struct TcAttnArgs {
   const bf16* vt;     // (B,H,hdv,T)
   bf16* out;          // [B*T, H*hd]
   int B, H, T, hd, hdp, hdv;
+  int experiment;     // developer timing experiments (VAVAE_ATTN_EXPERIMENT), 0 in production
 };
 void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s);
 bool pdl_enabled(cudaStream_t s);

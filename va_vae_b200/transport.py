@@ -442,9 +442,9 @@ class Sampler:
             applies elementwise (cos / sin of the 'decreasing' forms may differ in the last bit between CPU and GPU)."""
             t = th.ones(1, device=device) * ti
             diffusion = diffusion_fn(t.view(1, 1), t)
-            diffusion = diffusion if th.is_tensor(diffusion) else th.tensor(float(diffusion))
             sigma_t = 1 - t
             var = sigma_t ** 2 - (t / 1) * (-1) * sigma_t
+            # form "constant" yields a python float and th.sqrt then raises, exactly as in the reference (integrators.py:37)
             return dict(t=float(t), diffusion=float(diffusion), var=float(var),
                         sqrt_2diffusion=float(th.sqrt(2 * diffusion)), sqrt_dt=float(th.sqrt(dt)))
 
