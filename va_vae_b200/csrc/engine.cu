@@ -60,6 +60,8 @@ struct vavae_engine {
   float* ada_b = nullptr;     // [NM]
   // packed (bf16 mode)
   float* rope_cs = nullptr;   // [T, hd/2, 2] interleaved (cos, sin) when the tables repeat each frequency twice
+  float* rope_tab = nullptr;  // [2, gw, hd/4, 2] compact form when the tables are also separable over the token grid
+  int rope_gw = 0;
   bf16* ada_w_h = nullptr;    // [NM, D]
   bf16* final_w_h = nullptr;  // [Pout, D]
   std::vector<LayerBf16> lw;
@@ -208,6 +210,39 @@ __global__ void k_fill_ones_row(bf16* vt, int BH, int hdv, int row, int T) {
   if (idx >= BH * T) return;
   int bh = idx / T, t = idx % T;
   vt[((size_t)bh * hdv + row) * T + t] = __float2bfloat16_rn(1.0f);
+}
+
+// RoPE tables of the state_dict, (T, hd) cos / sin on the host -> the two packed forms the QKV epilogue reads:
+//   cs  [T][hd/2][2]  one (cos, sin) per rotation pair, valid when every frequency is repeated twice (pos_embed.py:123-128)
+//   tab [2][gw][hd/4][2]  additionally separable over the gw x gw token grid: first-half pairs depend on the grid row,
+//                         second-half pairs on the grid column (pos_embed.py:121-128).  Both are verified bit for bit
+//                         against the full tables; an empty vector means "not of that form".
+static void pack_rope_tables(const std::vector<float>& hc, const std::vector<float>& hs, int T, int hd, std::vector<float>& cs,
+                             std::vector<float>& tab, int& gw) {
+  cs.clear(); tab.clear(); gw = 0;
+  if (hd % 2) return;
+  for (size_t i = 0; i < hc.size(); i += 2)
+    if (hc[i] != hc[i + 1] || hs[i] != hs[i + 1]) return;
+  cs.resize((size_t)T * hd);
+  for (size_t i = 0; i < hc.size(); i += 2) { cs[i] = hc[i]; cs[i + 1] = hs[i]; }
+  int g = (int)std::lround(std::sqrt((double)T));
+  if (g * g != T || g < 4 || hd % 4) return;
+  const int hq = hd / 4, hp = hd / 2;
+  std::vector<float> t2((size_t)2 * g * hq * 2);
+  for (int pos = 0; pos < g; ++pos)
+    for (int q = 0; q < hq; ++q)
+      for (int e = 0; e < 2; ++e) {
+        t2[((size_t)(0 * g + pos) * hq + q) * 2 + e] = cs[((size_t)(pos * g) * hp + q) * 2 + e];        // token (pos, 0)
+        t2[((size_t)(1 * g + pos) * hq + q) * 2 + e] = cs[((size_t)pos * hp + hq + q) * 2 + e];          // token (0, pos)
+      }
+  for (int t = 0; t < T; ++t)
+    for (int r = 0; r < hp; ++r)
+      for (int e = 0; e < 2; ++e) {
+        const int pos = r < hq ? t / g : t % g, q = r < hq ? r : r - hq;
+        if (cs[((size_t)t * hp + r) * 2 + e] != t2[((size_t)((r < hq ? 0 : 1) * g + pos) * hq + q) * 2 + e]) return;
+      }
+  tab.swap(t2);
+  gw = g;
 }
 
 static void pack_bf16(vavae_engine* e, const float* src, bf16* dst, int rows, int K, int ldo, int interleave_S,
@@ -370,16 +405,17 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
   if (!e->fp32 && c.use_rope && hd % 2 == 0) {
     // RoPE tables of the reference repeat every frequency twice (pos_embed.py:123-128): if this state_dict's do too,
     // keep one (cos, sin) pair per rotation pair -> half the table traffic in the QKV epilogue
-    std::vector<float> hc((size_t)T * hd), hs((size_t)T * hd);
+    std::vector<float> hc((size_t)T * hd), hs((size_t)T * hd), cs, tab;
     VV_CUDA(cudaMemcpy(hc.data(), e->W("feat_rope.freqs_cos").d, hc.size() * 4, cudaMemcpyDeviceToHost));
     VV_CUDA(cudaMemcpy(hs.data(), e->W("feat_rope.freqs_sin").d, hs.size() * 4, cudaMemcpyDeviceToHost));
-    bool paired = true;
-    for (size_t i = 0; i < hc.size() && paired; i += 2) paired = hc[i] == hc[i + 1] && hs[i] == hs[i + 1];
-    if (paired) {
-      std::vector<float> cs((size_t)T * hd);
-      for (size_t i = 0; i < hc.size(); i += 2) { cs[i] = hc[i]; cs[i + 1] = hs[i]; }
+    pack_rope_tables(hc, hs, T, hd, cs, tab, e->rope_gw);
+    if (!cs.empty()) {
       e->rope_cs = e->alloc<float>(cs.size());
       VV_CUDA(cudaMemcpy(e->rope_cs, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (!tab.empty()) {
+      e->rope_tab = e->alloc<float>(tab.size());
+      VV_CUDA(cudaMemcpy(e->rope_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     }
   }
   if (!e->fp32) {
@@ -622,7 +658,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
     } else {
       const float* bqkv = e->W(blk(i, "attn.qkv.bias")).d;
       TcGemmArgs a = tc_args(e->A_h, D, e->lw[i].qkv, D, M, 3 * D, D, TC_EPI_QKV, bqkv);
-      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
+      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.rope_tab = e->rope_tab; a.rope_gw = e->rope_gw; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
       a.kn_b = knb; a.qk_rms = c.use_rmsnorm; a.H = H; a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
       if (fuse && i > 0) {
         a.in_part = e->part2; a.in_nparts = np_w3; a.in_dim = D;
@@ -1309,19 +1345,23 @@ int vavae_test_gemm_epilogue(vavae_epilogue_test_t* t, void* stream) {
       a.q = (bf16*)t->q; a.k = (bf16*)t->k; a.vt = (bf16*)t->vt; a.cos = t->cos; a.sin = t->sin; a.qn_w = t->qn_w; a.kn_w = t->kn_w;
       a.qk_rms = 1; a.H = t->H; a.hd = t->hd; a.hdp = ((t->hd + 15) / 16) * 16; a.hdv = attention_hdv(t->hd);
       if (t->cos && t->sin && t->hd % 2 == 0) {
-        // same repack as vavae_finalize: one (cos, sin) pair per rotation pair when the tables repeat each frequency twice
+        // same packing as vavae_finalize
         const size_t nel = (size_t)t->T * t->hd;
-        std::vector<float> hc(nel), hs(nel), cs(nel);
+        std::vector<float> hc(nel), hs(nel), cs, tab;
         VV_CUDA(cudaStreamSynchronize(s));
         VV_CUDA(cudaMemcpy(hc.data(), t->cos, nel * 4, cudaMemcpyDeviceToHost));
         VV_CUDA(cudaMemcpy(hs.data(), t->sin, nel * 4, cudaMemcpyDeviceToHost));
-        bool paired = true;
-        for (size_t i = 0; i < nel && paired; i += 2) paired = hc[i] == hc[i + 1] && hs[i] == hs[i + 1];
-        if (paired) {
-          for (size_t i = 0; i < nel; i += 2) { cs[i] = hc[i]; cs[i + 1] = hs[i]; }
-          VV_CUDA(cudaMalloc(&rope_cs, nel * 4));
+        int gw = 0;
+        pack_rope_tables(hc, hs, t->T, t->hd, cs, tab, gw);
+        if (!cs.empty()) {
+          VV_CUDA(cudaMalloc(&rope_cs, (nel + tab.size()) * 4));
           VV_CUDA(cudaMemcpy(rope_cs, cs.data(), nel * 4, cudaMemcpyHostToDevice));
           a.rope_cs = rope_cs;
+          if (!tab.empty()) {
+            VV_CUDA(cudaMemcpy(rope_cs + nel, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+            a.rope_tab = rope_cs + nel;
+            a.rope_gw = gw;
+          }
         }
       }
     } else if (t->kind == VAVAE_EPI_SWIGLU) {
@@ -1390,7 +1430,7 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     *work = 2.0 * M * 3.0 * D * D;
     fn = [&] {
       TcGemmArgs a = tc_args(e->A_h, D, e->lw[0].qkv, D, M, 3 * D, D, TC_EPI_QKV, e->W(blk(0, "attn.qkv.bias")).d);
-      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.qk_rms = c.use_rmsnorm; a.H = H;
+      a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.rope_tab = e->rope_tab; a.rope_gw = e->rope_gw; a.qk_rms = c.use_rmsnorm; a.H = H;
       a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
       if (c.use_qknorm) { a.qn_w = e->W(blk(0, "attn.q_norm.weight")).d; a.kn_w = e->W(blk(0, "attn.k_norm.weight")).d; }
       if (fused) {   // as launched for layers >= 1: 1/rms from the previous w3's partial sums, per-sample sp vector

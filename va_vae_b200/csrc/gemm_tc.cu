@@ -217,7 +217,7 @@ template <int EPI>
 __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_t st_s, const uint32_t tbase,
                                               uint64_t* tfull, const uint32_t aphase, const int m0, const int n0,
                                               const int n_blk, const int BN, const int q, const int half,
-                                              const int lane) {
+                                              const int lane, const uint32_t rope_s) {
   constexpr int CW = 32, LPR = 8, RPP = 4, SST = (CW + 4) * 4;  // staging row stride in bytes
   const int prow = lane >> 3, pcc = (lane & 7) * 4;
   const int wrow0 = m0 + q * 32;
@@ -287,28 +287,13 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
 #pragma unroll
   for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
 
-  // QKV: head index / in-head offset by multiply-high (exact for col * hd < 2^32) instead of integer division, and
-  // the interleaved RoPE table rows of this lane kept in registers, (re)loaded at the end of the previous chunk and
-  // only when the in-head offset changes (head_dim 64: a warp sees the same offsets in every q/k chunk of a tile)
+  // QKV: head index / in-head offset by multiply-high (exact for col * hd < 2^32) instead of integer division
   const int qD = EPI == TC_EPI_QKV ? a.H * a.hd : 1;
   const uint32_t hd_magic = EPI == TC_EPI_QKV ? 0xFFFFFFFFu / (uint32_t)a.hd + 1u : 0u;
-  float4 cs_n[LPR];
-  int cs_key = -1;
-  auto prefetch_cs = [&](int c) {
-    if (c >= n_chunks) return;
-    const int colc = n0 + c * CW;
-    const int which = (colc >= qD) + (colc >= 2 * qD);
-    if (which == 2) return;
-    const int rem = colc + pcc - which * qD;
-    const int d = rem - (int)__umulhi((uint32_t)rem, hd_magic) * a.hd;
-    if (d == cs_key) return;
-    cs_key = d;
-    const float* cs = a.rope_cs + ((size_t)(wt0 + prow) * (a.hd >> 1) + (d >> 1)) * 2;
-    const size_t tpass = (size_t)RPP * a.hd;  // (hd/2 pairs) * 2 floats per token
-#pragma unroll
-    for (int ps = 0; ps < LPR; ++ps) cs_n[ps] = *reinterpret_cast<const float4*>(cs + ps * tpass);
-  };
-  if (EPI == TC_EPI_QKV && a.rope_cs) prefetch_cs(half);
+  // compact RoPE tables in shared memory: grid row / column of this lane's token in pass 0 (tokens advance by RPP per pass)
+  const int gw = EPI == TC_EPI_QKV ? a.rope_gw : 1, hq = EPI == TC_EPI_QKV ? (a.hd >> 2) : 1;
+  int rp_i0 = 0, rp_j0 = 0;
+  if (EPI == TC_EPI_QKV && rope_s) { rp_i0 = (wt0 + prow) / gw; rp_j0 = (wt0 + prow) - rp_i0 * gw; }
 
   ptx::mbar_wait(tfull, aphase);
   ptx::tc_fence_after();
@@ -446,8 +431,37 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         const int rem = colc + pcc - which * D, h = (int)__umulhi((uint32_t)rem, hd_magic), d = rem - h * a.hd;
         bf16* dst = (which == 0 ? a.q : a.k) + (((size_t)wb * a.H + h) * a.T + wt0 + prow) * a.hdp + d;
         const size_t dpass = (size_t)RPP * a.hdp;
-        if (a.rope_cs) {
-          // interleaved (cos, sin) per rotation pair, held in cs_n (see prefetch_cs)
+        if (rope_s) {
+          // (cos, sin) of this lane's two rotation pairs from the shared-memory tables: pair r < hd/4 rotates by the
+          // token's grid row, pair r >= hd/4 by its grid column
+          const int r0 = d >> 1, r1 = r0 + 1;
+          const uint32_t b0 = rope_s + (uint32_t)((r0 < hq ? r0 : gw * hq + r0 - hq) * 8);
+          const uint32_t b1 = rope_s + (uint32_t)((r1 < hq ? r1 : gw * hq + r1 - hq) * 8);
+          const bool c0 = r0 >= hq, c1 = r1 >= hq;
+          int ti = rp_i0, tj = rp_j0;
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) {
+            float2 cs0, cs1;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cs0.x), "=f"(cs0.y) : "r"(b0 + (uint32_t)((c0 ? tj : ti) * hq * 8)));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cs1.x), "=f"(cs1.y) : "r"(b1 + (uint32_t)((c1 ? tj : ti) * hq * 8)));
+            float4 v = lds128(st_r + ps * RPP * SST);
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+            float4 o;
+            o.x = v.x * cs0.x - v.y * cs0.y;
+            o.y = v.y * cs0.x + v.x * cs0.y;
+            o.z = v.z * cs1.x - v.w * cs1.y;
+            o.w = v.w * cs1.x + v.z * cs1.y;
+            *reinterpret_cast<uint2*>(dst + ps * dpass) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+            tj += RPP;
+            if (tj >= gw) { tj -= gw; ++ti; }
+          }
+        } else if (a.rope_cs) {
+          // tables that are not separable over the token grid: interleaved (cos, sin) per rotation pair from global memory
+          const float* cs = a.rope_cs + ((size_t)(wt0 + prow) * (a.hd >> 1) + (d >> 1)) * 2;
+          const size_t tpass = (size_t)RPP * a.hd;  // (hd/2 pairs) * 2 floats per token
+          float4 cs_n[LPR];
+#pragma unroll
+          for (int ps = 0; ps < LPR; ++ps) cs_n[ps] = *reinterpret_cast<const float4*>(cs + ps * tpass);
 #pragma unroll
           for (int ps = 0; ps < LPR; ++ps) {
             float4 v = lds128(st_r + ps * RPP * SST);
@@ -491,8 +505,6 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         }
         }
       }
-      // table rows of this warp's next q/k chunk (a no-op while the in-head offset stays the same)
-      if (a.rope_cs) prefetch_cs(c + 2);
     }
   };
   if (kBiasAhead) {
@@ -617,6 +629,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int sched_n = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   float* staging = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
   TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(reinterpret_cast<uint8_t*>(staging) + 8 * 32 * (CW + 4) * 4);
+  // QKV: compact RoPE tables (a few KB of constants) live in shared memory for the whole kernel
+  float* rope_tab_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
+  const bool rope_smem = EPI == TC_EPI_QKV && a.rope_tab != nullptr;
+  if (rope_smem) {
+    const int n4 = a.rope_gw * (a.hd >> 2);   // float4 count: 2 tables * gw * hd/4 pairs * 2 floats / 4
+    for (int i = threadIdx.x; i < n4; i += TC_THREADS)
+      reinterpret_cast<float4*>(rope_tab_s)[i] = reinterpret_cast<const float4*>(a.rope_tab)[i];
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (a.M + tile_m - 1) / tile_m;
@@ -772,7 +792,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (CW == 32 && fast_ok && (bn_t % 32 == 0) && m0 + TC_BM <= a.M && n0 + bn_t <= a.N) {
         // interior tile of a production epilogue: guard-free path
         epi_tile_fast<EPI>(a, ptx::smem_u32(st), tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256,
-                           &bars->tfull[as], aphase, m0, n0, n_blk, bn_t, q, half, lane);
+                           &bars->tfull[as], aphase, m0, n0, n_blk, bn_t, q, half, lane,
+                           rope_smem ? ptx::smem_u32(rope_tab_s) : 0u);
         release_acc(as);
         as ^= 1;
         if (as == 0) aphase ^= 1;
@@ -1227,7 +1248,8 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
   const int BNlast = gemm_tc_last_bn(a, BN);
   const int b_rows = TWO ? BN / 2 : BN;
   const int stage_bytes = TC_A_BYTES + b_rows * 128;
-  const int fixed = 8 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024;
+  const int rope_bytes = (EPI == TC_EPI_QKV && a.rope_tab) ? 2 * a.rope_gw * (a.hd / 4) * 8 + 16 : 0;
+  const int fixed = 8 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024 + rope_bytes;
   int nstages = (227 * 1024 - fixed) / stage_bytes;
   if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
   VV_CHECK(nstages >= 2, "gemm_tc: tile too large for shared memory");
@@ -1328,6 +1350,18 @@ void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
     case TC_EPI_GELU_BF16: launch_epi<TC_EPI_GELU_BF16>(a, BN, cw, s); break;
     case TC_EPI_QKV:
       VV_CHECK(a.hd % 8 == 0 && (a.H * a.hd) % 16 == 0, "qkv epilogue: head_dim % 8 and hidden % 16 required");
+      VV_CHECK(!a.rope_tab || (a.rope_gw >= 4 && a.rope_gw * a.rope_gw == a.T && a.rope_gw * (a.hd / 4) * 16 <= 32 * 1024),
+               "qkv epilogue: compact RoPE tables need a square token grid of width >= 4 and at most 32 KB");
+      {
+        static int rope_smem = -1;   // VAVAE_ROPE_SMEM=0: developer knob, RoPE rows from global memory (same-box A/B)
+        if (rope_smem < 0) { const char* e = std::getenv("VAVAE_ROPE_SMEM"); rope_smem = (e && e[0] == '0') ? 0 : 1; }
+        if (!rope_smem && a.rope_tab) {
+          TcGemmArgs b = a;
+          b.rope_tab = nullptr;
+          launch_epi<TC_EPI_QKV>(b, BN, cw, s);
+          break;
+        }
+      }
       launch_epi<TC_EPI_QKV>(a, BN, cw, s);
       break;
     case TC_EPI_FINAL: launch_epi<TC_EPI_FINAL>(a, BN, cw, s); break;

@@ -33,6 +33,12 @@ struct TcGemmArgs {
   const float *cos, *sin;  // [T, hd] or null
   const float* rope_cs;    // optional [T, hd/2, 2] interleaved (cos, sin) per rotation pair: half the table traffic;
                            // only valid when the (T, hd) tables repeat every frequency twice (the reference's do)
+  // optional compact form of the same tables when they are separable over the token grid (the reference's are:
+  // columns [0, hd/2) depend on the token's grid row only, [hd/2, hd) on its grid column, pos_embed.py:121-128):
+  // rope_tab[0][pos][q] = (cos, sin) of rotation pair q < hd/4 at grid row pos, rope_tab[1][pos][q] = pair hd/4 + q at
+  // grid column pos; 2 * rope_gw * (hd/4) * 2 floats, kept in shared memory by the QKV epilogue (no L2 traffic)
+  const float* rope_tab;
+  int rope_gw;
   const float *qn_w, *qn_b, *kn_w, *kn_b;
   int qk_rms;
   int H, hd, hdp, hdv;
