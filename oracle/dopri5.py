@@ -1,12 +1,19 @@
 """TEST INFRASTRUCTURE ONLY -- restatement of torchdiffeq's adaptive `dopri5` (the un-vendored, un-pinned dependency the
 reference reaches at LightningDiT/transport/integrators.py:118-125 with method="dopri5", atol=1e-6, rtol=1e-3).
 
-PARITY UNPINNED for this solver: torchdiffeq is not installed here and not under /root/reference, so this file restates
-its published algorithm from the package's documented behaviour (Dormand-Prince 5(4) tableau with FSAL; Hairer initial
-step with order 4; RMS error norm over the whole state; step factor min(10, max(0.9 / ratio^(1/5), dfactor)) with
-dfactor 1 after an accepted step and 0.2 after a rejected one; float64 time / step size, state-dtype stage arithmetic;
-4th-order dense output, output points obtained by interpolation inside the accepted step that covers them).
-It is the checker for `vavae_sample_dopri5`; if torchdiffeq is ever importable, `tests/test_dopri5.py` cross-checks it.
+PARITY STATUS: torchdiffeq itself is not installed here and not under /root/reference, so this file restates its
+published algorithm (Dormand-Prince 5(4) tableau with FSAL; Hairer initial step with order 4; RMS error norm over the
+whole state; step factor min(10, max(0.9 / ratio^(1/5), dfactor)) with dfactor 1 after an accepted step and 0.2 after a
+rejected one; float64 time / step size, state-dtype stage arithmetic; 4th-order dense output, output points obtained by
+interpolation inside the accepted step that covers them).  It is PINNED AGAINST AN INDEPENDENT THIRD-PARTY
+IMPLEMENTATION of the same method, scipy.integrate.RK45 (tests/test_dopri5_scipy.py): the tableau, one full RK step, the
+error norm and the initial step agree with scipy's own primitives to round-off; a driver made of scipy's primitives plus
+the controller restated here reproduces this file's accepted / rejected step sequence and solution exactly, on an
+analytic ODE and on a tiny LightningDiT drift; stock RK45 agrees on the solution within the tolerance.  What that
+cross-check cannot cover, because scipy differs there by design, is restated from torchdiffeq's documentation only:
+its embedded error weights are 2/3 of the textbook b5 - b4 (asserted: C_ERR == -2/3 * scipy's E), an accepted step never
+shrinks the next one, and the last step is not clipped to t1.  If torchdiffeq is ever importable,
+tests/test_dopri5.py cross-checks against it directly.  This file is the checker for `vavae_sample_dopri5`.
 """
 import torch
 

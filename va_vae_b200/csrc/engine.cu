@@ -1493,6 +1493,25 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
       o.dt = 0.f; o.stage = 0;
       launch_ode_update(o, s);
     };
+  } else if (k == "patchify") {
+    ensure_state(e, rows);
+    const int Cpp = e->C * e->p * e->p;
+    *work = (double)rows * e->C * e->img * e->img * 4.0 + (double)M * 3.0 * Cpp * 2.0;  // bytes: read latents, write split-bf16 patches
+    RowMap rm;
+    rm.seg_rows = rows; rm.x_off[0] = rm.x_off[1] = 0; rm.y_off[0] = rm.y_off[1] = 0; rm.t_off[0] = rm.t_off[1] = 0;
+    rm.out_off[0] = rm.out_off[1] = 0; rm.t_stride = 0;
+    fn = [&, rm] { launch_patchify_split3(e->sx, e->Aemb_h, rows, e->C, e->img, e->p, T, rm, s); };
+  } else if (k == "cfg_combine") {
+    ensure_state(e, rows);
+    VV_CHECK(rows % 2 == 0, "cfg_combine needs an even number of rows");
+    *work = (double)rows * e->C * e->img * e->img * 4.0 * 2.0;  // bytes: read v, write out
+    VV_CUDA(cudaMemsetAsync(e->st, 0, 16, s));
+    fn = [&] {
+      CfgArgs cc;
+      cc.v = e->sv; cc.out = e->sxp; cc.t = e->st; cc.n = rows / 2; cc.C = e->C; cc.HW = e->img * e->img; cc.scale = 4.0f;
+      cc.interval = 0; cc.start = 0.f; cc.channels = 3;
+      launch_cfg_combine(cc, s);
+    };
   } else {
     throw Error("time_kernel: unknown kernel '" + k + "'");
   }

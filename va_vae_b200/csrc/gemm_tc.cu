@@ -261,8 +261,10 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
     const int colv = n0 + c * CW + pcc;
     if (bvec) bb_n = *reinterpret_cast<const float4*>(bvec + colv);
     if (EPI == TC_EPI_GATED_RESIDUAL) {
+      if (!(a.experiment & 1)) {
 #pragma unroll
       for (int ps = 0; ps < LPR; ++ps) xpre[ps] = *reinterpret_cast<const float4*>(xptr + ps * xpass + c * CW);
+      }
       g_n = *reinterpret_cast<const float4*>(modrow + a.gate_off + colv);
       if (a.nx_w) {
         nw_n = *reinterpret_cast<const float4*>(a.nx_w + colv);
@@ -295,6 +297,21 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   int rp_i0 = 0, rp_j0 = 0;
   if (EPI == TC_EPI_QKV && rope_s) { rp_i0 = (wt0 + prow) / gw; rp_j0 = (wt0 + prow) - rp_i0 * gw; }
 
+  // SwiGLU gates in the thread == row domain (the gated pair sits in adjacent accumulator columns of one thread), so
+  // only the bf16 result goes through the shared-memory transposition: a quarter of the staging traffic of the fp32
+  // block - and shared-memory bandwidth (operand fill + tensor-core reads + staging) is what bounds these kernels.
+  // The per-column bias / per-sample vectors of this warp's <= 4 chunks are parked behind the staging rows.
+  constexpr int HST = 48;                           // bf16 staging row stride in bytes (32 B of data, conflict-free 16-byte stores)
+  const uint32_t hb_s = st_s + 32 * HST;            // [4 chunks][32 columns] fp32
+  if (EPI == TC_EPI_SWIGLU) {
+    __syncwarp();                                   // the previous tile's row pass has finished reading this warp's staging area
+    if (prow == 0) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) sts128(hb_s + ci * 128 + pcc * 4, bball[ci].x, bball[ci].y, bball[ci].z, bball[ci].w);
+    }
+    __syncwarp();
+  }
+
   ptx::mbar_wait(tfull, aphase);
   ptx::tc_fence_after();
 
@@ -302,6 +319,35 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
     const int c0 = c * CW;
     uint32_t r[CW];
     ptx::tmem_ld_x32(tbase + c0, r);
+    if (EPI == TC_EPI_SWIGLU) {
+      const uint32_t bsrc = hb_s + (uint32_t)((c - half) >> 1) * 128;
+      float4 b4[CW / 4];
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) b4[j] = lds128(bsrc + j * 16);   // same address in every lane: broadcast
+      ptx::tmem_ld_wait();
+      uint32_t h[CW / 4];
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float v0 = __uint_as_float(r[4 * j]) * in_rstd + b4[j].x, v1 = __uint_as_float(r[4 * j + 1]) * in_rstd + b4[j].y;
+        const float v2 = __uint_as_float(r[4 * j + 2]) * in_rstd + b4[j].z, v3 = __uint_as_float(r[4 * j + 3]) * in_rstd + b4[j].w;
+        h[j] = pack_bf16(silu_fast(v0) * v1, silu_fast(v2) * v3);        // swiglu_ffn.py:33-35 on interleaved rows
+      }
+      __syncwarp();
+      const uint32_t hw = st_s + (uint32_t)lane * HST;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hw), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hw + 16), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+      __syncwarp();
+      // row pass: two lanes per row (16 bytes = 8 outputs each), 16 rows per store instruction
+      bf16* ho = reinterpret_cast<bf16*>(a.out) + (size_t)(wrow0 + (lane >> 1)) * a.ldo + ((n0 + c0) >> 1) + (lane & 1) * 8;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(st_s + (uint32_t)((it * 16 + (lane >> 1)) * HST + (lane & 1) * 16)) : "memory");
+        *reinterpret_cast<uint4*>(ho + (size_t)it * 16 * a.ldo) = v;
+      }
+      return;
+    }
     float4 xcur[LPR];
     if (EPI == TC_EPI_GATED_RESIDUAL) {
 #pragma unroll
@@ -329,9 +375,10 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         float4 x = xcur[ps];
         x.x = fmaf(g1.x, v.x + bb.x, x.x); x.y = fmaf(g1.y, v.y + bb.y, x.y);
         x.z = fmaf(g1.z, v.z + bb.z, x.z); x.w = fmaf(g1.w, v.w + bb.w, x.w);
-        *reinterpret_cast<float4*>(xo + ps * xpass) = x;
+        if (!(a.experiment & 4)) *reinterpret_cast<float4*>(xo + ps * xpass) = x;
         if (a.nx_w) {
           ssacc[ps] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+          if (!(a.experiment & 2))
           *reinterpret_cast<uint2*>(nxptr + c0 + ps * xpass) =
               make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
         }
@@ -632,6 +679,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // QKV: compact RoPE tables (a few KB of constants) live in shared memory for the whole kernel
   float* rope_tab_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
   const bool rope_smem = EPI == TC_EPI_QKV && a.rope_tab != nullptr;
+
   if (rope_smem) {
     const int n4 = a.rope_gw * (a.hd >> 2);   // float4 count: 2 tables * gw * hd/4 pairs * 2 floats / 4
     for (int i = threadIdx.x; i < n4; i += TC_THREADS)
@@ -1292,7 +1340,12 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
     VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, false>, tmA, tmB, tmBl, a, BN, BNlast, nstages));
   } else {
     const int tiles = cdiv(a.M, 2 * TC_BM) * cdiv(a.N, BN);
-    const int pairs = std::min(tiles, num_sms() / 2);
+    int pairs = std::min(tiles, num_sms() / 2);
+    {
+      static int max_pairs = -1;   // VAVAE_GEMM_MAX_PAIRS: developer experiment (is the operand feed limited per SM or chip-wide?)
+      if (max_pairs < 0) { const char* e = std::getenv("VAVAE_GEMM_MAX_PAIRS"); max_pairs = e ? std::atoi(e) : 0; }
+      if (max_pairs > 0) pairs = std::min(pairs, max_pairs);
+    }
     cfg.gridDim = dim3(2 * pairs);
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;
@@ -1345,7 +1398,14 @@ void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   switch (a.epi) {
     case TC_EPI_BIAS_F32: launch_epi<TC_EPI_BIAS_F32>(a, BN, cw, s); break;
     case TC_EPI_BIAS_BF16: launch_epi<TC_EPI_BIAS_BF16>(a, BN, cw, s); break;
-    case TC_EPI_GATED_RESIDUAL: launch_epi<TC_EPI_GATED_RESIDUAL>(a, BN, cw, s); break;
+    case TC_EPI_GATED_RESIDUAL: {
+      static int exp_mode = -1;
+      if (exp_mode < 0) { const char* e = std::getenv("VAVAE_GEMM_EXPERIMENT"); exp_mode = e ? std::atoi(e) : 0; }
+      TcGemmArgs b = a;
+      b.experiment = exp_mode;
+      launch_epi<TC_EPI_GATED_RESIDUAL>(b, BN, cw, s);
+      break;
+    }
     case TC_EPI_SWIGLU: launch_epi<TC_EPI_SWIGLU>(a, BN, cw, s); break;
     case TC_EPI_GELU_BF16: launch_epi<TC_EPI_GELU_BF16>(a, BN, cw, s); break;
     case TC_EPI_QKV:

@@ -74,6 +74,9 @@ struct TcGemmArgs {
   // (M % 128 == 0, N % tile width == 0): launch_gemm_tc checks it.
   float* gn_part;
   int gn_hw, gn_cpg_shift;
+  // developer timing experiments on the gated-residual epilogue (VAVAE_GEMM_EXPERIMENT; results are WRONG when set):
+  // bit 0: no residual loads, bit 1: no next-operand stores, bit 2: no residual stores.  0 in production.
+  int experiment;
 };
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
