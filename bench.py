@@ -351,10 +351,12 @@ def run_engine(args):
     clk = clocks.stop() if clocks else None
     value = n_total * args.steps / (ms / 1e3)
 
-    k_e2e = max(1, min(args.steps, args.e2e_steps))
-    step_e2e(wgrid)
-    ms_e2e = timed(step_e2e, k_e2e)
-    e2e_value = n_total * k_e2e / (ms_e2e / 1e3)
+    k_e2e = min(args.steps, args.e2e_steps)
+    e2e_value = None
+    if k_e2e > 0:                       # --e2e-steps 0: developer runs that only need the resident number
+        step_e2e(wgrid)
+        ms_e2e = timed(step_e2e, k_e2e)
+        e2e_value = n_total * k_e2e / (ms_e2e / 1e3)
 
     pk = peaks()
     flops_fwd = O.flops_per_forward(cfg)

@@ -537,7 +537,12 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   VV_CHECK(smem <= 227 * 1024, "attention: shared memory budget exceeded");
   const int sms = num_sms();
   const int n_items = a.B * a.H * cdiv(a.T, AT_BQ);
-  const int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  {
+    static int cap = -1;   // VAVAE_ATTN_PER_SM=1: developer experiment (do the two co-resident CTAs overlap?)
+    if (cap < 0) { const char* e = std::getenv("VAVAE_ATTN_PER_SM"); cap = e ? std::atoi(e) : 0; }
+    if (cap > 0) per_sm = std::min(per_sm, cap);
+  }
   const int grid = std::min(n_items, sms * per_sm);
   const bool multi = a.T > AT_BKV;
   TcAttnArgs aa = a;
