@@ -1169,19 +1169,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // ------------------------------------------------------------------------------------------------ host launch
-// Programmatic dependent launch for the tcgen05 kernels: opt-in with VAVAE_PDL=1 (an A/B on B200 showed no gain at the
-// benchmark batch sizes: 858-861 TFLOP/s either way, the persistent kernels' tails are short); never used while a
-// stream is being captured into a CUDA graph.
+// Programmatic dependent launch for the tcgen05 kernels (VAVAE_PDL: bit 0 = eager launches, bit 1 = launches captured
+// into the small-batch CUDA graphs; default 2).  Eager launches at the benchmark batch sizes gain nothing (858-861 TFLOP/s
+// either way: the persistent kernels' tails are short); inside the small-batch graphs, where a forward is ~230 kernels of
+// ~10 us each, overlapping each prologue (barrier init, TMEM allocation, tensor-map prefetch) with the predecessor's
+// tail is worth 1 - 4 % (XL/1 batch 1: 2.59 -> 2.48 ms, profiles/r2_small_batch.md).
 bool pdl_enabled(cudaStream_t s) {
   static int on = -1;
   if (on < 0) {
     const char* e = std::getenv("VAVAE_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;
+    on = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;   // bit 0: eager launches, bit 1: captured launches (default)
   }
   if (!on) return false;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
-  return st == cudaStreamCaptureStatusNone;
+  return st == cudaStreamCaptureStatusNone ? (on & 1) != 0 : (on & 2) != 0;
 }
 
 // Per-device state: function attributes and the SM count belong to a device (context), not to the process - a second
