@@ -173,7 +173,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (lane == 0) {
       // step = (item, blk) flattened; loads for a step: K (+Q on the first block of an item), and V
       auto load_qk = [&](int item, int blk) {
-        const int bh = item / nq, q0 = (item % nq) * AT_BQ, kv0 = blk * AT_BKV;
+        const int it_ = a.reverse ? n_items - 1 - item : item;
+        const int bh = it_ / nq, q0 = (it_ % nq) * AT_BQ, kv0 = blk * AT_BKV;
         ptx::mbar_expect_tx(&bars->qk_full, (uint32_t)(g.k_bytes + (blk == 0 ? g.q_bytes : 0)));
         for (int ka = 0; ka < g.n_full; ++ka) {
           ptx::tma_load_3d(sK + ka * AT_BKV * 128, &tmK, &bars->qk_full, ka * 64, kv0, bh);
@@ -185,7 +186,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       };
       auto load_v = [&](int item, int blk) {
-        const int bh = item / nq, kv0 = blk * AT_BKV;
+        const int it_ = a.reverse ? n_items - 1 - item : item;
+        const int bh = it_ / nq, kv0 = blk * AT_BKV;
         ptx::mbar_expect_tx(&bars->v_full, (uint32_t)g.v_bytes);
         for (int kk = 0; kk < 4; ++kk) ptx::tma_load_3d(sV + kk * g.v_atom, &tmV, &bars->v_full, kv0 + kk * 64, 0, bh);
       };
@@ -258,7 +260,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int ncol_o = a.hd + 1;                                   // head_dim columns + the row-sum column
     uint32_t step = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int bh = item / nq, q0 = (item % nq) * AT_BQ;
+      const int it_ = a.reverse ? n_items - 1 - item : item;
+      const int bh = it_ / nq, q0 = (it_ % nq) * AT_BQ;
       float m_run = -INFINITY;
       float oacc[MULTI ? OACC : 1];
 #pragma unroll

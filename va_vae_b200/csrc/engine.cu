@@ -46,6 +46,8 @@ struct vavae_engine {
   std::vector<void*> owned;  // everything cudaMalloc'ed by the engine
   uint64_t bytes = 0;
   LaunchCounter counter;
+  int alt_order = 1;         // alternate the row-tile order of consecutive layer kernels (VAVAE_ALT_ORDER=0 disables)
+  int order = 0;             // direction of the next layer kernel
   uint64_t fwd_rows = 0;     // model rows pushed through the layer stack since creation (executed forwards)
   int* err_flag = nullptr;   // device flag: a label outside [0, label_rows) was seen (vavae_device_status)
   // live per-kernel profiling (bench.py roofline): CUDA event pairs around every launch of one kernel class
@@ -593,6 +595,14 @@ static void conditioning(vavae_engine* e, int rows, const RowMap& rm, const floa
   }
 }
 
+// Direction of the next layer kernel: consecutive kernels walk the rows in opposite directions, so each one starts on
+// the rows its predecessor produced last (the tail of a larger-than-L2 tensor that is still cached).
+static int next_order(vavae_engine* e) {
+  if (!e->alt_order) return 0;
+  e->order ^= 1;
+  return e->order;
+}
+
 static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const float* x, const float* t, const int64_t* y,
                           float* out, cudaStream_t s) {
   const int D = e->D, T = e->T, H = e->H, hd = e->hd, S = e->S, L = e->L;
@@ -600,6 +610,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
   const vavae_config_t& c = e->cfg;
   VV_CHECK(rows <= e->chunk_rows, "forward_chunk: chunk larger than workspace");
   e->fwd_rows += (uint64_t)rows;
+  e->order = 0;   // every forward starts from the same state: captured graphs and eager launches behave identically
   const int Cpp = e->C * e->p * e->p;
   if (!e->fp32 && (3 * Cpp) % 8 == 0) {
     // patch embed on the tensor cores: split-bf16 patches x [W_hi | W_hi | W_lo], fp32-grade; epilogue adds bias + pos
@@ -666,6 +677,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       }
       {
         ProfScope ps(e, PK_QKV, 2.0 * M * 3.0 * D * D, s);
+        a.reverse_m = next_order(e);
         launch_gemm_tc(a, s);
       }
       TcAttnArgs at;
@@ -673,6 +685,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       at.hdp = e->hdp; at.hdv = e->hdv;
       {
         ProfScope ps(e, PK_ATTN, 4.0 * rows * (double)H * T * T * hd, s);
+        at.reverse = next_order(e);
         launch_attention_tc(at, s);
       }
       TcGemmArgs pr = tc_args(e->O_h, D, e->lw[i].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(i, "attn.proj.bias")).d);
@@ -683,6 +696,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       }
       {
         ProfScope ps(e, PK_PROJ, 2.0 * M * (double)D * D, s);
+        pr.reverse_m = next_order(e);
         launch_gemm_tc(pr, s);
       }
     }
@@ -715,6 +729,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
           a.sp = sp_mlp ? sp_mlp : e->lw[i].b1; a.sp_ld = sp_mlp ? e->NMx : 0;
         }
         ProfScope ps(e, PK_W12, 2.0 * M * (c.use_swiglu ? 2.0 : 1.0) * S * D, s);
+        a.reverse_m = next_order(e);
         launch_gemm_tc(a, s);
       }
       const float* b2 = e->W(blk(i, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d;
@@ -727,6 +742,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       }
       {
         ProfScope ps(e, PK_W3, 2.0 * M * (double)S * D, s);
+        a.reverse_m = next_order(e);
         launch_gemm_tc(a, s);
       }
     }
@@ -1108,6 +1124,7 @@ int vavae_create(const vavae_config_t* cfg, int device, vavae_engine_t** out) {
     e->device = device;
     derive(e);
     if (const char* gm = std::getenv("VAVAE_GRAPH_MAX_ROWS")) e->graph_max_rows = std::atoi(gm);
+    if (const char* ao = std::getenv("VAVAE_ALT_ORDER")) e->alt_order = std::atoi(ao);
     *out = e;
     return 0;
   } catch (const std::exception& ex) {

@@ -729,7 +729,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
         const bool last_n = n_blk == n_tiles - 1 && BNlast != BN;   // narrower last column tile
         const int bn_t = last_n ? BNlast : BN;
         const int b_rows_t = TWO ? bn_t / 2 : bn_t;
@@ -834,7 +834,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       else ptx::mbar_arrive(&bars->tempty[stage_idx]);
     };
     for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
       const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
       const int bn_t = (n_blk == n_tiles - 1) ? BNlast : BN;   // columns of this tile
       if (CW == 32 && fast_ok && (bn_t % 32 == 0) && m0 + TC_BM <= a.M && n0 + bn_t <= a.N) {

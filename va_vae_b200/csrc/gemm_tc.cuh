@@ -77,6 +77,10 @@ struct TcGemmArgs {
   // developer timing experiments on the gated-residual epilogue (VAVAE_GEMM_EXPERIMENT; results are WRONG when set):
   // bit 0: no residual loads, bit 1: no next-operand stores, bit 2: no residual stores.  0 in production.
   int experiment;
+  // Row-tile order: 0 = ascending, 1 = descending.  The engine alternates it from one kernel of the layer stack to the
+  // next so that a consumer starts on the rows its producer wrote LAST - the part of a larger-than-L2 tensor that is
+  // still cached.  Results do not depend on it (no atomics, fixed partial-sum slots).
+  int reverse_m;
 };
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
@@ -90,7 +94,8 @@ struct TcAttnArgs {
   const bf16* vt;     // (B,H,hdv,T)
   bf16* out;          // [B*T, H*hd]
   int B, H, T, hd, hdp, hdv;
-  int experiment;     // developer timing experiments (VAVAE_ATTN_EXPERIMENT), 0 in production
+  int experiment = 0; // developer timing experiments (VAVAE_ATTN_EXPERIMENT), 0 in production
+  int reverse = 0;    // 1: work items in descending order (see TcGemmArgs::reverse_m)
 };
 void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s);
 bool pdl_enabled(cudaStream_t s);
