@@ -4,14 +4,22 @@
 // blocks of 256 with an online softmax.  Per block ("step"):
 //   S = Q K^T   : tcgen05.mma  M=128, N=keys (<=256), K=hd padded to 16         -> TMEM columns [0,256)
 //   softmax     : 128 threads, thread == query row; S read with tcgen05.ld; p = ex2.approx.ftz.f32 (one MUFU op
-//                 per probability), packed to bf16 pairs and written straight back into TMEM
-//   P           : bf16, two per 32-bit TMEM column, aliasing S columns [0,128); TMEM A-operand of the second MMA
-//   O = P V     : tcgen05.mma  M=128, N=hdv, K=keys                              -> TMEM columns [128,128+hdv)
+//                 per probability), TRUNCATED to bf16 pairs by one PRMT (F2FP would share the XU pipe with MUFU; the
+//                 truncation bias cancels in the normalisation, see ex2_trunc_bf16x2) and written straight back into TMEM
+//   P           : bf16, two per 32-bit TMEM column, aliasing dead S columns; TMEM A-operand of the second MMA
+//   O = P V     : tcgen05.mma  M=128, N=hdv, K=keys.  For a full 256-key block the MMA over the first 192 keys is
+//                 issued while the last 64 keys are still being exponentiated (barrier p_part; O then sits at
+//                 columns [96, 96+hdv) and the last two P chunks stay in place at columns 192 / 224)
 //   row sums    : V^T carries a row of ones at index hd, so column hd of O *is* sum_j P_ij (exactly the bf16
 //                 probabilities the MMA consumed) - no summation instructions in the softmax loop.
+//   output      : normalised rows are packed to bf16 into a [128][hd] tile in the idle V^T buffer and written by ONE
+//                 TMA store per item (cp.async.bulk.tensor, full lines) - row-strided 16-byte st.global from the
+//                 thread == row domain cost 12 % of the kernel in LSU time.
 // TMA loads are software-pipelined across steps with single buffers: Q/K of step s+1 are requested as soon as
-// the S MMA of step s retires, V of step s+1 as soon as the P V MMA of step s retires, so their latency hides
-// behind the softmax of step s.  The second CTA on the SM fills the tensor/MUFU pipes meanwhile.
+// the S MMA of step s retires and S of step s+1 is issued as soon as the softmax threads have read O of step s;
+// V of step s+1 is requested once the P V MMA of step s has retired (and, on an item's last block, once the output
+// store has read the staging tile), so every load hides behind a softmax.  The second CTA on the SM fills the
+// tensor / MUFU pipes meanwhile.
 //
 // Layouts (all K-major TMA tiles, 128-byte swizzle): q,k (B,H,T,hdp); v transposed (B,H,hdv,T), written by the
 // QKV GEMM epilogue.  A 16-column tail of hdp (head_dim 72 -> 80) is loaded as a compact 32-byte-swizzled tile.
@@ -31,7 +39,7 @@ constexpr int AT_BKV = 256;  // keys per step
 constexpr int AT_THREADS = 160;
 
 struct AtBars {
-  uint64_t qk_full, v_full, s_full, p_full, o_full, o_empty, qk_empty, v_empty;
+  uint64_t qk_full, v_full, s_full, p_full, p_part, o_full, o_empty, o_staged, qk_empty, v_empty;
   uint32_t tmem_base;
 };
 
@@ -104,6 +112,21 @@ __device__ __forceinline__ uint32_t ex2_pack_bf16x2(float x0, float x1) {
   return out;
 }
 
+// Same, but the pair is packed by TRUNCATION (one PRMT on the ALU pipe instead of F2FP, which shares the 16-lane XU
+// pipe with MUFU).  The row sum is taken from the very probabilities the MMA consumes (ones row of V^T), so the mean
+// relative bias of truncation (-2^-8) cancels in O = sum(p v) / sum(p); what is left has the variance of round-to-nearest.
+__device__ __forceinline__ uint32_t ex2_trunc_bf16x2(float x0, float x1) {
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(x0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(x1));
+  return __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 struct AtGeom {
   int n_full;     // number of full 64-column atoms of Q/K
   int tail16;     // 1: a compact 16-column tail tile follows the full atoms
@@ -126,7 +149,8 @@ template <int OACC>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQt,
-               const __grid_constant__ CUtensorMap tmKt, const TcAttnArgs a) {
+               const __grid_constant__ CUtensorMap tmKt, const __grid_constant__ CUtensorMap tmO,
+               const TcAttnArgs a) {
   constexpr bool MULTI = OACC > 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -141,18 +165,26 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int nblk = (a.T + AT_BKV - 1) / AT_BKV;
   const int n_items = a.B * a.H * nq;
   constexpr uint32_t TMEM_COLS = 256;
-  constexpr uint32_t O_COL = 128;
+  // O accumulator columns.  Generic blocks: P compact in [0,128), O at 128 (aliasing dead S columns).  Full 256-key
+  // blocks in early-PV mode: P of key chunks 0..5 compact in [0,96), O at 96, P of chunks 6 / 7 in place at 192 / 224,
+  // so the P V MMA over the first 192 keys runs while the last two chunks are still being exponentiated.
+  constexpr uint32_t O_COL_GENERIC = 128, O_COL_EARLY = 96;
+  const bool early_ok = !(a.experiment & 8) && a.hdv <= 96;
+  const bool trunc_pack = !(a.experiment & 4);
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
+    ptx::prefetch_tmap(&tmO);
     ptx::mbar_init(&bars->qk_full, 1);
     ptx::mbar_init(&bars->v_full, 1);
     ptx::mbar_init(&bars->s_full, 1);
     ptx::mbar_init(&bars->p_full, 128);
+    ptx::mbar_init(&bars->p_part, 128);
     ptx::mbar_init(&bars->o_full, 1);
     ptx::mbar_init(&bars->o_empty, 128);
+    ptx::mbar_init(&bars->o_staged, 128);
     ptx::mbar_init(&bars->qk_empty, 1);
     ptx::mbar_init(&bars->v_empty, 1);
     ptx::fence_barrier_init();
@@ -191,66 +223,101 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         ptx::mbar_expect_tx(&bars->v_full, (uint32_t)g.v_bytes);
         for (int kk = 0; kk < 4; ++kk) ptx::tma_load_3d(sV + kk * g.v_atom, &tmV, &bars->v_full, kv0 + kk * 64, 0, bh);
       };
-      uint32_t step = 0;
+      // S = Q K^T of one step (keys [blk*256, ...) of an item)
+      auto issue_s = [&](int blk) {
+        const int kvlen = min(AT_BKV, a.T - blk * AT_BKV);
+        const uint32_t idesc = ptx::make_idesc_bf16(AT_BQ, ((kvlen + 15) / 16) * 16);
+        int ks = 0;
+        for (int ka = 0; ka < g.n_full; ++ka) {
+          const int kmax = min(4, (a.hdp - ka * 64) / 16);
+          for (int kin = 0; kin < kmax; ++kin, ++ks) {
+            const uint64_t ad = ptx::make_desc_k_sw128(ptx::smem_u32(sQ + ka * AT_BQ * 128)) + (uint64_t)(kin * 2);
+            const uint64_t bd = ptx::make_desc_k_sw128(ptx::smem_u32(sK + ka * AT_BKV * 128)) + (uint64_t)(kin * 2);
+            ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
+          }
+        }
+        if (g.tail16) {
+          const uint64_t ad = make_desc_k_sw32(ptx::smem_u32(sQ + g.n_full * AT_BQ * 128));
+          const uint64_t bd = make_desc_k_sw32(ptx::smem_u32(sK + g.n_full * AT_BKV * 128));
+          ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
+        }
+        ptx::umma_commit(&bars->s_full);
+        ptx::umma_commit(&bars->qk_empty);
+      };
+      uint32_t step = 0, items_done = 0;
       if ((int)blockIdx.x < n_items) {
         load_qk(blockIdx.x, 0);
         load_v(blockIdx.x, 0);
+        ptx::mbar_wait(&bars->qk_full, 0);
+        ptx::tc_fence_after();
+        issue_s(0);
       }
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         for (int blk = 0; blk < nblk; ++blk, ++step) {
+          // the S MMA of this step is already in flight (issued at the end of the previous step)
           const uint32_t ph = step & 1;
           const int kvlen = min(AT_BKV, a.T - blk * AT_BKV);
-          const int n_s = ((kvlen + 15) / 16) * 16;  // MMA N for S / K extent of P V
-          // next step (for prefetch)
-          int nitem = item, nblkk = blk + 1;
+          const int n_s = ((kvlen + 15) / 16) * 16;  // K extent of P V
+          int nitem = item, nblkk = blk + 1;          // next step (for prefetch)
           if (nblkk == nblk) { nitem = item + gridDim.x; nblkk = 0; }
           const bool has_next = nitem < n_items;
 
-          ptx::mbar_wait(&bars->qk_full, ph);
-          if (step > 0) ptx::mbar_wait(&bars->o_empty, ph ^ 1);  // softmax threads drained the previous O / P
-          ptx::tc_fence_after();
-          {  // S = Q K^T
-            const uint32_t idesc = ptx::make_idesc_bf16(AT_BQ, n_s);
-            int ks = 0;
-            for (int ka = 0; ka < g.n_full; ++ka) {
-              const int kmax = min(4, (a.hdp - ka * 64) / 16);
-              for (int kin = 0; kin < kmax; ++kin, ++ks) {
-                const uint64_t ad = ptx::make_desc_k_sw128(ptx::smem_u32(sQ + ka * AT_BQ * 128)) + (uint64_t)(kin * 2);
-                const uint64_t bd = ptx::make_desc_k_sw128(ptx::smem_u32(sK + ka * AT_BKV * 128)) + (uint64_t)(kin * 2);
-                ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
-              }
-            }
-            if (g.tail16) {
-              const uint64_t ad = make_desc_k_sw32(ptx::smem_u32(sQ + g.n_full * AT_BQ * 128));
-              const uint64_t bd = make_desc_k_sw32(ptx::smem_u32(sK + g.n_full * AT_BKV * 128));
-              ptx::umma_bf16_ss(tmem_base, ad, bd, idesc, (uint32_t)(ks != 0));
-            }
-            ptx::umma_commit(&bars->s_full);
-            ptx::umma_commit(&bars->qk_empty);
-          }
           // Q/K tiles are free once S retires: request the next step's Q/K now (hidden behind this softmax)
           ptx::mbar_wait(&bars->qk_empty, ph);
           if (has_next) load_qk(nitem, nblkk);
 
           // O_blk = P V
           ptx::mbar_wait(&bars->v_full, ph);
-          ptx::mbar_wait(&bars->p_full, ph);
-          ptx::tc_fence_after();
           {
             const uint32_t idesc = ptx::make_idesc_bf16(AT_BQ, a.hdv);
             const int ksteps = n_s / 16;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            const bool early = early_ok && kvlen == AT_BKV;
+            const uint32_t o_col = early ? O_COL_EARLY : O_COL_GENERIC;
+            auto pv = [&](int ks, uint32_t pcol) {
               const int atom = ks >> 2, kin = ks & 3;
               const uint64_t bd = ptx::make_desc_k_sw128(ptx::smem_u32(sV + atom * g.v_atom)) + (uint64_t)(kin * 2);
-              umma_bf16_ts(tmem_base + O_COL, tmem_base + (uint32_t)(ks * 8), bd, idesc, (uint32_t)(ks != 0));
+              umma_bf16_ts(tmem_base + o_col, tmem_base + pcol, bd, idesc, (uint32_t)(ks != 0));
+            };
+            if (early) {
+              ptx::mbar_wait(&bars->p_part, ph);   // probabilities of keys [0,192) are in TMEM
+              ptx::tc_fence_after();
+              for (int ks = 0; ks < 12; ++ks) pv(ks, (uint32_t)(ks * 8));
+              ptx::mbar_wait(&bars->p_full, ph);
+              ptx::tc_fence_after();
+              pv(12, 192); pv(13, 200); pv(14, 224); pv(15, 232);
+            } else {
+              if (early_ok) ptx::mbar_wait(&bars->p_part, ph);   // keeps the barrier's phase in step
+              ptx::mbar_wait(&bars->p_full, ph);
+              ptx::tc_fence_after();
+              for (int ks = 0; ks < ksteps; ++ks) pv(ks, (uint32_t)(ks * 8));
             }
             ptx::umma_commit(&bars->o_full);
             ptx::umma_commit(&bars->v_empty);
           }
           ptx::mbar_wait(&bars->v_empty, ph);
+          // next step's S as soon as its Q/K have landed and the softmax threads have read this step's O
+          if (has_next) {
+            ptx::mbar_wait(&bars->qk_full, ph ^ 1);
+            ptx::mbar_wait(&bars->o_empty, ph);
+            ptx::tc_fence_after();
+            issue_s(nblkk);
+          }
+          if (blk == nblk - 1) {
+            // the item's output rows, normalised and packed to bf16, are staged in the (now idle) V^T buffer by the
+            // softmax threads: one TMA store writes them as full lines; V^T of the next step is requested once the
+            // store has read the buffer (it is not needed before that step's P V, a whole softmax away)
+            const int it_ = a.reverse ? n_items - 1 - item : item;
+            const int bh = it_ / nq, q0 = (it_ % nq) * AT_BQ;
+            ptx::mbar_wait(&bars->o_staged, items_done & 1);
+            ++items_done;
+            ptx::tma_store_4d(&tmO, sV, 0, bh % a.H, q0, bh / a.H);
+            ptx::tma_store_commit();
+            ptx::tma_store_wait_read0();
+          }
           if (has_next) load_v(nitem, nblkk);
         }
       }
+      ptx::tma_store_wait_all();
     }
   } else {
     // ------------------------------------------------------------- softmax / output threads (thread == query row)
@@ -258,6 +325,16 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float sl2 = rsqrtf((float)a.hd) * 1.4426950408889634f;  // scale * log2(e)
     const int ncol_o = a.hd + 1;                                   // head_dim columns + the row-sum column
+    // output staging: row-major [128][hd] bf16 in the V^T buffer (idle between the last P V of an item and the next V^T
+    // load); 16-byte chunks are XOR-swizzled like the tensor map when a row is exactly 128 bytes (conflict-free stores;
+    // a 144-byte row pitch is conflict-free as it is)
+    const uint32_t stage_row = ptx::smem_u32(sV) + (uint32_t)row * (uint32_t)(a.hd * 2);
+    const uint32_t stage_xor = (a.hd == 64) ? (uint32_t)(row & 7) : 0u;
+    auto stage16 = [&](int chunk, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + (((uint32_t)chunk ^ stage_xor) << 4)),
+                   "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                   : "memory");
+    };
     uint32_t step = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int it_ = a.reverse ? n_items - 1 - item : item;
@@ -275,7 +352,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         ptx::mbar_wait(&bars->s_full, ph);
         ptx::tc_fence_after();
         float m_new, alpha, moff;
-        if (n_s == AT_BKV && !ragged) {
+        const bool full_blk = n_s == AT_BKV && !ragged;
+        const uint32_t o_col = (early_ok && full_blk) ? O_COL_EARLY : O_COL_GENERIC;
+        if (full_blk) {
           // ---- full 256-key block: fully unrolled, TMEM loads software-pipelined (load chunk i+1 while reducing /
           //      exponentiating chunk i; two 32-register buffers)
           uint32_t ra[32], rb[32];
@@ -312,12 +391,25 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             uint32_t* nxt = (i & 1) ? ra : rb;
             if (i < 7) ptx::tmem_ld_x32(trow + (uint32_t)((i + 1) * 32), nxt);
             uint32_t pk[16];
+            if (trunc_pack) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2)
-              pk[j >> 1] = ex2_pack_bf16x2(fmaf(__uint_as_float(cur[j]), sl2, -moff),
-                                           fmaf(__uint_as_float(cur[j + 1]), sl2, -moff));
+              for (int j = 0; j < 32; j += 2)
+                pk[j >> 1] = ex2_trunc_bf16x2(fmaf(__uint_as_float(cur[j]), sl2, -moff),
+                                              fmaf(__uint_as_float(cur[j + 1]), sl2, -moff));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2)
+                pk[j >> 1] = ex2_pack_bf16x2(fmaf(__uint_as_float(cur[j]), sl2, -moff),
+                                             fmaf(__uint_as_float(cur[j + 1]), sl2, -moff));
+            }
             if (i < 7) tmem_ld_wait_dep32(nxt);   // the next chunk is in registers before P overwrites its S columns
-            tmem_st_x16(trow + (uint32_t)(i * 16), pk);
+            // early-PV mode: chunks 6 / 7 stay in place (columns 192 / 224) - O occupies [96, 96 + hdv)
+            tmem_st_x16(trow + (uint32_t)((early_ok && i >= 6) ? i * 32 : i * 16), pk);
+            if (early_ok && i == 5) {
+              tmem_st_wait();
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&bars->p_part);
+            }
           }
         } else {
         // ---- generic block (fewer than 256 keys and / or a ragged tail)
@@ -374,6 +466,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         m_run = m_new;
         tmem_st_wait();
         ptx::tc_fence_before();
+        if (early_ok && !full_blk) ptx::mbar_arrive(&bars->p_part);
         ptx::mbar_arrive(&bars->p_full);
 
         // O block (and, in column hd, the row sum of the probabilities the MMA consumed)
@@ -383,29 +476,20 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (!MULTI) {
           // single block: normalise and store straight from TMEM.  All O columns (and the row-sum column hd) are
           // requested first and waited for once; TMEM is released before the global stores.
-          const int b = bh / a.H, h = bh % a.H;
-          const bool valid = (q0 + row) < a.T;
-          bf16* orow = a.out + ((size_t)b * a.T + q0 + row) * ((size_t)a.H * a.hd) + (size_t)h * a.hd;
           const int ncol = ((a.hd >> 4) + 1) << 4;   // 16-column groups up to and including the one holding column hd
-          auto store8 = [&](const uint32_t* r8, int c, float inv) {   // 8 consecutive columns -> one 16-byte store
-            if (!valid || c >= a.hd) return;
-            uint4 pk;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(r8[0]) * inv, __uint_as_float(r8[1]) * inv);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(r8[2]) * inv, __uint_as_float(r8[3]) * inv);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(r8[4]) * inv, __uint_as_float(r8[5]) * inv);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(r8[6]) * inv, __uint_as_float(r8[7]) * inv);
-            pk.x = *reinterpret_cast<uint32_t*>(&t0);
-            pk.y = *reinterpret_cast<uint32_t*>(&t1);
-            pk.z = *reinterpret_cast<uint32_t*>(&t2);
-            pk.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(orow + c) = pk;
+          auto store8 = [&](const uint32_t* r8, int c, float inv) {   // 8 consecutive columns -> one 16-byte chunk
+            if (c >= a.hd) return;
+            stage16(c >> 3, pack_bf16x2(__uint_as_float(r8[0]) * inv, __uint_as_float(r8[1]) * inv),
+                    pack_bf16x2(__uint_as_float(r8[2]) * inv, __uint_as_float(r8[3]) * inv),
+                    pack_bf16x2(__uint_as_float(r8[4]) * inv, __uint_as_float(r8[5]) * inv),
+                    pack_bf16x2(__uint_as_float(r8[6]) * inv, __uint_as_float(r8[7]) * inv));
           };
           if (ncol == 80) {
             // head_dim 64 / 72 (every registry model): 80 columns in three loads, one wait, TMEM released early
             uint32_t o0[32], o1[32], o2[16];
-            ptx::tmem_ld_x32(trow + O_COL, o0);
-            ptx::tmem_ld_x32(trow + O_COL + 32, o1);
-            ptx::tmem_ld_x16(trow + O_COL + 64, o2);
+            ptx::tmem_ld_x32(trow + o_col, o0);
+            ptx::tmem_ld_x32(trow + o_col + 32, o1);
+            ptx::tmem_ld_x16(trow + o_col + 64, o2);
             tmem_ld_wait_dep32(o0);
             tmem_ld_wait_dep32(o1);
             tmem_ld_wait_dep16(o2);
@@ -420,12 +504,12 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             store8(o2, 64, inv);
           } else {
             uint32_t rl[16];
-            ptx::tmem_ld_x16(trow + O_COL + (uint32_t)((a.hd >> 4) << 4), rl);  // the 16-column group holding column hd
+            ptx::tmem_ld_x16(trow + o_col + (uint32_t)((a.hd >> 4) << 4), rl);  // the 16-column group holding column hd
             tmem_ld_wait_dep16(rl);
             const float inv = 1.0f / __uint_as_float((a.hd & 15) ? rl[8] : rl[0]);
             for (int c0 = 0; c0 < a.hd; c0 += 16) {
               uint32_t r[16];
-              ptx::tmem_ld_x16(trow + O_COL + c0, r);
+              ptx::tmem_ld_x16(trow + o_col + c0, r);
               tmem_ld_wait_dep16(r);
               store8(r, c0, inv);
               store8(r + 8, c0 + 8, inv);
@@ -438,9 +522,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (OACC == 80) {
             // head_dim 64 / 72: all 80 columns requested at once, one wait, TMEM released before the arithmetic
             uint32_t o0[32], o1[32], o2[16];
-            ptx::tmem_ld_x32(trow + O_COL, o0);
-            ptx::tmem_ld_x32(trow + O_COL + 32, o1);
-            ptx::tmem_ld_x16(trow + O_COL + 64, o2);
+            ptx::tmem_ld_x32(trow + o_col, o0);
+            ptx::tmem_ld_x32(trow + o_col + 32, o1);
+            ptx::tmem_ld_x16(trow + o_col + 64, o2);
             tmem_ld_wait_dep32(o0);
             tmem_ld_wait_dep32(o1);
             tmem_ld_wait_dep16(o2);
@@ -457,7 +541,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           } else {
           for (int c0 = 0; c0 < ncol_o; c0 += 16) {
             uint32_t r[16];
-            ptx::tmem_ld_x16(trow + O_COL + c0, r);
+            ptx::tmem_ld_x16(trow + o_col + c0, r);
             ptx::tmem_ld_wait();
             // oacc is only ever indexed with compile-time constants (fully unrolled, guarded by c0)
 #pragma unroll
@@ -477,25 +561,20 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int i = 0; i < OACC; ++i)
               if (i == a.hd) l = oacc[i];
             const float inv = 1.0f / l;
-            const int b = bh / a.H, h = bh % a.H;
-            const bool valid = (q0 + row) < a.T;
-            bf16* orow = a.out + ((size_t)b * a.T + q0 + row) * ((size_t)a.H * a.hd) + (size_t)h * a.hd;
 #pragma unroll
             for (int c8 = 0; c8 < OACC / 8; ++c8) {
-              if (c8 * 8 < a.hd && valid) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(oacc[c8 * 8 + 0] * inv, oacc[c8 * 8 + 1] * inv);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(oacc[c8 * 8 + 2] * inv, oacc[c8 * 8 + 3] * inv);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(oacc[c8 * 8 + 4] * inv, oacc[c8 * 8 + 5] * inv);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(oacc[c8 * 8 + 6] * inv, oacc[c8 * 8 + 7] * inv);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(orow + c8 * 8) = pk;
-              }
+              if (c8 * 8 < a.hd)
+                stage16(c8, pack_bf16x2(oacc[c8 * 8 + 0] * inv, oacc[c8 * 8 + 1] * inv),
+                        pack_bf16x2(oacc[c8 * 8 + 2] * inv, oacc[c8 * 8 + 3] * inv),
+                        pack_bf16x2(oacc[c8 * 8 + 4] * inv, oacc[c8 * 8 + 5] * inv),
+                        pack_bf16x2(oacc[c8 * 8 + 6] * inv, oacc[c8 * 8 + 7] * inv));
             }
           }
+        }
+        if (last) {
+          // the 128 output rows are staged: make them visible to the async proxy and hand them to the control thread
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&bars->o_staged);
         }
       }
     }
@@ -512,6 +591,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // 3-D bf16 tensor map with a caller-chosen swizzle (32-byte swizzle for the compact 16-column tail tiles)
 CUtensorMap make_tmap_3d_bf16_sw(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                                  uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
+CUtensorMap make_tmap_4d(const void* base, int elem_bytes, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                         const uint32_t box[4], int swizzle_bytes);
 
 int attention_hdv(int hd) { return ((hd + 1 + 15) / 16) * 16; }
 
@@ -536,6 +617,11 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
     tmKt = make_tmap_3d_bf16_sw(a.k, (uint64_t)a.hdp, (uint64_t)a.T, BH, (uint64_t)a.hdp * 2, (uint64_t)a.T * a.hdp * 2,
                                 16, AT_BKV, 1, 32);
   }
+  // output rows of one (batch, head, 128-query tile): box over (hd, H, T, B), written by TMA from the staging tile
+  const uint64_t odims[4] = {(uint64_t)a.hd, (uint64_t)a.H, (uint64_t)a.T, (uint64_t)a.B};
+  const uint64_t ostr[3] = {(uint64_t)a.hd * 2, (uint64_t)a.H * a.hd * 2, (uint64_t)a.T * a.H * a.hd * 2};
+  const uint32_t obox[4] = {(uint32_t)a.hd, 1u, (uint32_t)std::min(AT_BQ, a.T), 1u};
+  CUtensorMap tmO = make_tmap_4d(a.out, 2, odims, ostr, obox, a.hd == 64 ? 128 : 0);
   const size_t smem = (size_t)((g.q_bytes + 1023) & ~1023) + ((g.k_bytes + 1023) & ~1023) + g.v_bytes + sizeof(AtBars) + 1024;
   VV_CHECK(smem <= 227 * 1024, "attention: shared memory budget exceeded");
   const int sms = num_sms();
@@ -575,9 +661,9 @@ void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  if (multi && a.hd + 1 <= 80) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<80>, tmQ, tmK, tmV, tmQt, tmKt, aa));
-  else if (multi) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<128>, tmQ, tmK, tmV, tmQt, tmKt, aa));
-  else VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<0>, tmQ, tmK, tmV, tmQt, tmKt, aa));
+  if (multi && a.hd + 1 <= 80) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<80>, tmQ, tmK, tmV, tmQt, tmKt, tmO, aa));
+  else if (multi) VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<128>, tmQ, tmK, tmV, tmQt, tmKt, tmO, aa));
+  else VV_CUDA(cudaLaunchKernelEx(&cfg, k_attention_tc<0>, tmQ, tmK, tmV, tmQt, tmKt, tmO, aa));
   VV_LAUNCH_CHECK();
 }
 

@@ -142,6 +142,33 @@ CUtensorMap make_tmap_3d_bf16_sw(const void* base, uint64_t d0, uint64_t d1, uin
   });
 }
 
+// General 4-D tiled map (bf16 or fp32 elements; swizzle_bytes 0 = none / 128).  Used for TMA STORES of output tiles
+// (attention output rows of one head, residual-stream tiles); out-of-bounds parts of a box are not written.
+CUtensorMap make_tmap_4d(const void* base, int elem_bytes, const uint64_t dims_[4], const uint64_t strides_bytes[3],
+                         const uint32_t box_[4], int swizzle_bytes) {
+  const TmapKey key = {{6, (uint64_t)(uintptr_t)base, dims_[0] | (dims_[1] << 32), dims_[2] | (dims_[3] << 32),
+                        strides_bytes[0], strides_bytes[1], strides_bytes[2],
+                        (uint64_t)box_[0] | ((uint64_t)box_[1] << 16) | ((uint64_t)box_[2] << 32) | ((uint64_t)box_[3] << 48),
+                        (uint64_t)swizzle_bytes, (uint64_t)elem_bytes, 0, 0}};
+  return cached_tmap(key, [&] {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {dims_[0], dims_[1], dims_[2], dims_[3]};
+  cuuint64_t strides[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t box[4] = {box_[0], box_[1], box_[2], box_[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  VV_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && strides[0] % 16 == 0 && strides[1] % 16 == 0 &&
+               strides[2] % 16 == 0 && ((uint64_t)box[0] * elem_bytes) % 16 == 0,
+           "tensor map (4d) alignment");
+  VV_CHECK(swizzle_bytes == 0 || (int)box[0] * elem_bytes <= swizzle_bytes, "tensor map (4d): inner box wider than the swizzle span");
+  CUresult r = get_encode()(&m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                            const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled(4d) failed with code " + std::to_string((int)r));
+  return m;
+  });
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;

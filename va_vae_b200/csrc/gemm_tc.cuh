@@ -94,7 +94,9 @@ struct TcAttnArgs {
   const bf16* vt;     // (B,H,hdv,T)
   bf16* out;          // [B*T, H*hd]
   int B, H, T, hd, hdp, hdv;
-  int experiment = 0; // developer timing experiments (VAVAE_ATTN_EXPERIMENT), 0 in production
+  // developer A/B knobs (VAVAE_ATTN_EXPERIMENT), 0 in production: 1 = no row-max pass (timing only, results wrong),
+  // 4 = round-to-nearest P pack (F2FP) instead of truncation, 8 = no early P V issue
+  int experiment = 0;
   int reverse = 0;    // 1: work items in descending order (see TcGemmArgs::reverse_m)
 };
 void launch_attention_tc(const TcAttnArgs& a, cudaStream_t s);
