@@ -117,10 +117,12 @@ def test_swiglu_epilogue(fused_norm, S):
 
 @pytest.mark.parametrize("N,K", [(384, 384), (1152, 3072), (768, 2048)])
 @pytest.mark.parametrize("next_norm", [False, True])
-def test_gated_residual_epilogue(N, K, next_norm):
+@pytest.mark.parametrize("T,Bn", [(256, 3), (256, 4), (160, 3)])
+def test_gated_residual_epilogue(N, K, next_norm, T, Bn):
+    """M = 768 / 1024 rows: whole 256-row tile pairs -> the TMA epilogue (residual tiles moved by cp.async.bulk.tensor);
+    M = 480: partial tiles -> the register-prefetch fast path plus the guarded path on the edge tile."""
     from va_vae_b200 import engine as E
     dev = _dev()
-    T, Bn = 256, 3
     M = Bn * T
     A, W, bias = _operands(M, N, K, seed=70 + N)
     X0 = _rand(M, N, seed=1)

@@ -181,6 +181,11 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
 }
+// x.x^2 + x.y^2 + x.z^2 + x.w^2 with a pinned contraction: every path that emits RMSNorm partial sums (generic, fast
+// and TMA epilogues) must round identically, or results would depend on which path a row's tile took
+__device__ __forceinline__ float sumsq4(const float4 x) {
+  return fmaf(x.w, x.w, fmaf(x.z, x.z, fmaf(x.y, x.y, x.x * x.x)));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -404,7 +409,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         x.z = fmaf(g1.z, v.z + bb.z, x.z); x.w = fmaf(g1.w, v.w + bb.w, x.w);
         if (!(a.experiment & 4)) *reinterpret_cast<float4*>(xo + ps * xpass) = x;
         if (a.nx_w) {
-          ssacc[ps] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+          ssacc[ps] += sumsq4(x);
           if (!(a.experiment & 2))
           *reinterpret_cast<uint2*>(nxptr + c0 + ps * xpass) =
               make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
@@ -602,11 +607,39 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ TMA epilogue
+// Gated residual with the residual stream moved by TMA (TC_EPI_GATED_RESIDUAL_TMA).  Per epilogue warp: a ring of two
+// 32 x 32 fp32 tiles (4 KB, 128-byte swizzle).  The tile of the NEXT chunk is in flight while the current one is
+// processed; the update happens in place in the thread == row domain (lane = accumulator row = tile row; the swizzle
+// makes 16-byte accesses of 32 different rows conflict-free), then one elected lane stores the tile - and the bf16
+// operand tile of the next GEMM - with cp.async.bulk.tensor.  Nothing of the residual stream goes through the LSU / L1
+// miss path, whose limited outstanding-miss capacity capped the register-prefetch epilogue at ~4 TB/s.
+// Same arithmetic as the other two paths: x' = fma(gate, acc + bias, x); operand = bf16(x' * w * (1 + scale));
+// partial sums of x'^2 in the same grouping and order (sumsq4 per 4 columns, 8 column groups combined as a butterfly).
+constexpr int XT_BYTES = 32 * 128;         // residual tile
+constexpr int NXT_BYTES = 32 * 64;         // bf16 operand tile
+constexpr int VEC_BYTES = 4 * 3 * 128;     // per warp: [4 chunks][bias | gate | w*(1+scale)][32 columns]
+constexpr int TMA_EPI_BYTES = 8 * (2 * XT_BYTES + NXT_BYTES + VEC_BYTES);
+
+// (the residual / operand tensor maps are encoded with rank 4 - make_tmap_4d - so the 4-D instruction forms are used)
+__device__ __forceinline__ void tma_load_tile(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(0)
+               : "memory");
+}
+
 struct TcSmemBars {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t xfull[8][2];   // TMA epilogue: residual-tile ring, [epilogue warp][slot]
   uint32_t tmem_base;
 };
 
@@ -691,7 +724,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
 template <int EPI, int CW, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          const __grid_constant__ CUtensorMap tmBl, const TcGemmArgs a, const int BN, const int BNlast,
+          const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmX,
+          const __grid_constant__ CUtensorMap tmNX, const TcGemmArgs a, const int BN, const int BNlast,
           const int nstages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -702,7 +736,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int sched_id = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int sched_n = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   float* staging = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
-  TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(reinterpret_cast<uint8_t*>(staging) + 8 * 32 * (CW + 4) * 4);
+  TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(
+      reinterpret_cast<uint8_t*>(staging) + (EPI == TC_EPI_GATED_RESIDUAL_TMA ? TMA_EPI_BYTES : 8 * 32 * (CW + 4) * 4));
   // QKV: compact RoPE tables (a few KB of constants) live in shared memory for the whole kernel
   float* rope_tab_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
   const bool rope_smem = EPI == TC_EPI_QKV && a.rope_tab != nullptr;
@@ -730,6 +765,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->tfull[i], 1);
       ptx::mbar_init(&bars->tempty[i], TWO ? 512 : 256);   // 2-CTA: both CTAs' epilogue threads release the leader
+    }
+    if (EPI == TC_EPI_GATED_RESIDUAL_TMA) {
+      ptx::prefetch_tmap(&tmX);
+      ptx::prefetch_tmap(&tmNX);
+      for (int i = 0; i < 8; ++i) {
+        ptx::mbar_init(&bars->xfull[i][0], 1);
+        ptx::mbar_init(&bars->xfull[i][1], 1);
+      }
     }
     ptx::fence_barrier_init();
   }
@@ -860,6 +903,119 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (TWO && rank != 0) ptx2::mbar_arrive_remote(&bars->tempty[stage_idx], 0);
       else ptx::mbar_arrive(&bars->tempty[stage_idx]);
     };
+    if (EPI == TC_EPI_GATED_RESIDUAL_TMA) {
+      // every tile is interior and the warp's 32 rows belong to one sample (launch_gemm_tc checked it)
+      const int ew = warp - 2;
+      const uint32_t epi_s = ptx::smem_u32(staging);
+      const uint32_t xs = epi_s + (uint32_t)ew * (2 * XT_BYTES);
+      const uint32_t nxs = epi_s + 8 * 2 * XT_BYTES + (uint32_t)ew * NXT_BYTES;
+      const uint32_t vs = epi_s + 8 * (2 * XT_BYTES + NXT_BYTES) + (uint32_t)ew * VEC_BYTES;
+      uint64_t* xbar = bars->xfull[ew];
+      const bool has_nx = a.nx_w != nullptr;
+      // this warp's (tile, chunk) stream; `ld_*` runs two positions ahead of the chunk being processed
+      int ld_tile = sched_id, ld_c = half;
+      auto ld_issue = [&](int slot) {   // lane 0 only
+        if (ld_tile >= num_tiles) return;
+        const int mb = a.reverse_m ? m_tiles - 1 - ld_tile / n_tiles : ld_tile / n_tiles, nb = ld_tile % n_tiles;
+        const int row0 = mb * tile_m + (int)rank * TC_BM + q * 32, col0 = nb * BN + ld_c * 32;
+        ptx::mbar_expect_tx(&xbar[slot], XT_BYTES);
+        tma_load_tile(xs + (uint32_t)slot * XT_BYTES, &tmX, ptx::smem_u32(&xbar[slot]), col0, row0);
+        const int nch = ((nb == n_tiles - 1) ? BNlast : BN) >> 5;
+        ld_c += 2;
+        if (ld_c >= nch) { ld_tile += sched_n; ld_c = half; }
+      };
+      if (lane == 0) { ld_issue(0); ld_issue(1); }
+      uint32_t k = 0;   // position in the stream
+      for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
+        const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
+        const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
+        const int n_chunks = ((n_blk == n_tiles - 1) ? BNlast : BN) >> 5;
+        const int wrow0 = m0 + q * 32;
+        const int wb = wrow0 / a.T;
+        const float* modrow = a.mod + (size_t)wb * a.mod_ld;
+        // per-column vectors of this warp's chunks (lane = column): bias, gate, and the next norm's w * (1 + scale)
+        __syncwarp();
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = half + 2 * ci;
+          if (c < n_chunks) {
+            const int col = n0 + c * 32 + lane;
+            const float bv = a.bias ? a.bias[col] : 0.f;
+            const float gv = modrow[a.gate_off + col];
+            const float cv = has_nx ? a.nx_w[col] * (1.f + modrow[a.nx_scale_off + col]) : 0.f;
+            const uint32_t vb = vs + (uint32_t)(ci * 3) * 128 + (uint32_t)lane * 4;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb), "f"(bv) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 128), "f"(gv) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 256), "f"(cv) : "memory");
+          }
+        }
+        __syncwarp();
+        ptx::mbar_wait(&bars->tfull[as], aphase);
+        ptx::tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
+        float ss[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss[i] = 0.f;
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = half + 2 * ci;
+          if (c >= n_chunks) break;
+          const uint32_t slot = k & 1u;
+          const uint32_t xt = xs + slot * XT_BYTES + (uint32_t)lane * 128;
+          uint32_t r[32];
+          ptx::tmem_ld_x32(tbase + (uint32_t)(c * 32), r);
+          ptx::mbar_wait(&xbar[slot], (k >> 1) & 1u);   // the residual tile of this chunk has landed
+          ptx::tmem_ld_wait();
+          if (c + 2 >= n_chunks) release_acc(as);       // last read of this accumulator stage by this warp
+          uint32_t nxw[16];
+          const uint32_t vb = vs + (uint32_t)(ci * 3) * 128;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const uint32_t xa = xt + (uint32_t)((j4 ^ (lane & 7)) << 4);
+            float4 x = lds128(xa);
+            const float4 b4 = lds128(vb + j4 * 16), g4 = lds128(vb + 128 + j4 * 16);   // broadcast reads
+            x.x = fmaf(g4.x, __uint_as_float(r[j4 * 4]) + b4.x, x.x);
+            x.y = fmaf(g4.y, __uint_as_float(r[j4 * 4 + 1]) + b4.y, x.y);
+            x.z = fmaf(g4.z, __uint_as_float(r[j4 * 4 + 2]) + b4.z, x.z);
+            x.w = fmaf(g4.w, __uint_as_float(r[j4 * 4 + 3]) + b4.w, x.w);
+            sts128(xa, x.x, x.y, x.z, x.w);
+            if (has_nx) {
+              const float4 c4 = lds128(vb + 256 + j4 * 16);
+              ss[j4] += sumsq4(x);
+              nxw[j4 * 2] = pack_bf16(x.x * c4.x, x.y * c4.y);
+              nxw[j4 * 2 + 1] = pack_bf16(x.z * c4.z, x.w * c4.w);
+            }
+          }
+          if (has_nx) {
+            const uint32_t na = nxs + (uint32_t)lane * 64;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(na + jj * 16), "r"(nxw[jj * 4]),
+                           "r"(nxw[jj * 4 + 1]), "r"(nxw[jj * 4 + 2]), "r"(nxw[jj * 4 + 3])
+                           : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int col0 = n0 + c * 32;
+            tma_store_tile(&tmX, xs + slot * XT_BYTES, col0, wrow0);
+            if (has_nx) tma_store_tile(&tmNX, nxs, col0, wrow0);
+            ptx::tma_store_commit();
+            ptx::tma_store_wait_read0();   // both source tiles have been read: the slot takes the load two chunks ahead
+            ld_issue((int)slot);
+          }
+          __syncwarp();                    // no lane rewrites the operand tile before the store has read it
+          ++k;
+        }
+        if (has_nx) {
+          const float v = ((ss[0] + ss[4]) + (ss[2] + ss[6])) + ((ss[1] + ss[5]) + (ss[3] + ss[7]));
+          a.nx_part[(size_t)(wrow0 + lane) * 32 + (n_blk * 2 + half)] = v;
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+      if (lane == 0) ptx::tma_store_wait_all();
+    } else
     for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
       const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
@@ -1092,7 +1248,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             x.z = fmaf(g.z, v.z + bb.z, x.z); x.w = fmaf(g.w, v.w + bb.w, x.w);
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = x;
             if (a.nx_w) {
-              ssacc[ps] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+              ssacc[ps] += sumsq4(x);
               *reinterpret_cast<uint2*>(a.nx_A + (size_t)row * a.ldo + col) =
                   make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
             }
@@ -1247,7 +1403,7 @@ static int g_two_cta = 2;
 static bool want_two_cta(const TcGemmArgs& a) {
   if (g_two_cta == 0 || a.M < 2 * TC_BM) return false;
   if (g_two_cta >= 2) return true;
-  switch (a.epi) {
+  switch (a.epi == TC_EPI_GATED_RESIDUAL_TMA ? (int)TC_EPI_GATED_RESIDUAL : a.epi) {
     case TC_EPI_SWIGLU:
     case TC_EPI_GELU_BF16: return true;
     case TC_EPI_GATED_RESIDUAL: return a.K >= 2 * a.N;
@@ -1272,8 +1428,9 @@ static bool layer_gemm(const TcGemmArgs& a) {
   if (a.conv_taps || a.gn_part) return false;
   // attn.proj (K <= N, bandwidth-bound on its residual traffic) measured 3-4 % faster on 192-wide tiles: more, smaller
   // tiles keep more residual loads in flight; the main-loop-bound GEMMs want the wide tiles
-  if (a.epi == TC_EPI_GATED_RESIDUAL && a.K <= a.N && bn_mode() == 0) return false;
-  return a.epi == TC_EPI_GATED_RESIDUAL || a.epi == TC_EPI_SWIGLU || a.epi == TC_EPI_GELU_BF16 ||
+  const bool gated = a.epi == TC_EPI_GATED_RESIDUAL || a.epi == TC_EPI_GATED_RESIDUAL_TMA;
+  if (gated && a.K <= a.N && bn_mode() == 0) return false;
+  return gated || a.epi == TC_EPI_SWIGLU || a.epi == TC_EPI_GELU_BF16 ||
          (a.epi == TC_EPI_QKV && !a.qn_w && (a.H * a.hd) % 32 == 0);
 }
 // Width of the last column tile: the remainder when the problem is tiled 256-wide and the remainder is a whole number
@@ -1329,7 +1486,8 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
   const int b_rows = TWO ? BN / 2 : BN;
   const int stage_bytes = TC_A_BYTES + b_rows * 128;
   const int rope_bytes = (EPI == TC_EPI_QKV && a.rope_tab) ? 2 * a.rope_gw * (a.hd / 4) * 8 + 16 : 0;
-  const int fixed = 8 * 32 * (CW + 4) * 4 + (int)sizeof(TcSmemBars) + 1024 + rope_bytes;
+  const int epi_bytes = EPI == TC_EPI_GATED_RESIDUAL_TMA ? TMA_EPI_BYTES : 8 * 32 * (CW + 4) * 4;
+  const int fixed = epi_bytes + (int)sizeof(TcSmemBars) + 1024 + rope_bytes;
   int nstages = (227 * 1024 - fixed) / stage_bytes;
   if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
   VV_CHECK(nstages >= 2, "gemm_tc: tile too large for shared memory");
@@ -1353,6 +1511,18 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
   CUtensorMap tmBl = BNlast == BN ? tmB
                                   : make_tmap_2d_bf16(a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldw * 2, TC_BK,
                                                       (uint32_t)(TWO ? BNlast / 2 : BNlast));
+  // TMA epilogue: 32 x 32 tiles of the fp32 residual stream (128-byte swizzle) and of the next GEMM's bf16 operand
+  CUtensorMap tmX = tmA, tmNX = tmA;
+  if (EPI == TC_EPI_GATED_RESIDUAL_TMA) {
+    const uint64_t xd[4] = {(uint64_t)a.N, (uint64_t)a.M, 1, 1};
+    const uint64_t xstr[3] = {(uint64_t)a.ldo * 4, (uint64_t)a.ldo * 4 * a.M, (uint64_t)a.ldo * 4 * a.M};
+    const uint32_t xbox[4] = {32, 32, 1, 1};
+    tmX = make_tmap_4d(a.out, 4, xd, xstr, xbox, 128);
+    if (a.nx_w) {
+      const uint64_t nstr[3] = {(uint64_t)a.ldo * 2, (uint64_t)a.ldo * 2 * a.M, (uint64_t)a.ldo * 2 * a.M};
+      tmNX = make_tmap_4d(a.nx_A, 2, xd, nstr, xbox, 0);
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
@@ -1369,7 +1539,7 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
     cfg.gridDim = dim3(tiles < num_sms() ? tiles : num_sms());
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, false>, tmA, tmB, tmBl, a, BN, BNlast, nstages));
+    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, false>, tmA, tmB, tmBl, tmX, tmNX, a, BN, BNlast, nstages));
   } else {
     const int tiles = cdiv(a.M, 2 * TC_BM) * cdiv(a.N, BN);
     int pairs = std::min(tiles, num_sms() / 2);
@@ -1386,7 +1556,7 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
     ++na;
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, true>, tmA, tmB, tmBl, a, BN, BNlast, nstages));
+    VV_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<EPI, CW, true>, tmA, tmB, tmBl, tmX, tmNX, a, BN, BNlast, nstages));
   }
   VV_LAUNCH_CHECK();
 }
@@ -1435,7 +1605,23 @@ void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
       if (exp_mode < 0) { const char* e = std::getenv("VAVAE_GEMM_EXPERIMENT"); exp_mode = e ? std::atoi(e) : 0; }
       TcGemmArgs b = a;
       b.experiment = exp_mode;
-      launch_epi<TC_EPI_GATED_RESIDUAL>(b, BN, cw, s);
+      // the TMA epilogue needs guard-free geometry: whole 256-row tile pairs, whole 32-column chunks, 32-row groups
+      // inside one sample, 16-byte row pitches.  VAVAE_GEMM_TMA_EPI=0: developer knob (same-box A/B)
+      static int tma_epi = -1;
+      if (tma_epi < 0) { const char* e = std::getenv("VAVAE_GEMM_TMA_EPI"); tma_epi = e ? std::atoi(e) : 2; }
+      const int BNl = gemm_tc_last_bn(a, BN);
+      // 1: every eligible launch; 2 (default): only where the epilogue dominates (K <= N, attn.proj) - the TMA variant gives
+      // up one or two operand stages for its ring, which costs the main-loop-bound mlp.w3 more than its epilogue gains
+      const bool tma_ok = tma_epi && (tma_epi == 1 || a.K <= a.N) && exp_mode == 0 && cw == 32 && a.T > 0 && a.T % 32 == 0 && a.M % (2 * TC_BM) == 0 &&
+                          BN % 32 == 0 && BNl % 32 == 0 && (a.N % BN == 0 || a.N % BN == BNl) && a.ldo % 8 == 0 &&
+                          a.N <= a.ldo && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                          (!a.nx_w || (reinterpret_cast<uintptr_t>(a.nx_A) & 15) == 0) && a.mod != nullptr;
+      if (tma_ok) {
+        b.epi = TC_EPI_GATED_RESIDUAL_TMA;
+        launch_epi<TC_EPI_GATED_RESIDUAL_TMA>(b, BN, cw, s);
+      } else {
+        launch_epi<TC_EPI_GATED_RESIDUAL>(b, BN, cw, s);
+      }
       break;
     }
     case TC_EPI_SWIGLU: launch_epi<TC_EPI_SWIGLU>(a, BN, cw, s); break;

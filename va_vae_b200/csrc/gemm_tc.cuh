@@ -13,6 +13,10 @@ enum TcEpi {
   TC_EPI_QKV = 5,            // bias, [qk-norm], RoPE, scatter q,k (B,H,T,hdp) / v^T (B,H,hdv,T)
   TC_EPI_FINAL = 6,          // acc + bias -> unpatchify -> NCHW rows of the caller  (final_layer.linear)
   TC_EPI_EMBED = 7,          // out f32 [M, ldo] = acc + bias + pos[row % T]          (x_embedder + pos_embed)
+  // TC_EPI_GATED_RESIDUAL with the residual tile moved by TMA (loads into a shared-memory ring, in-place update,
+  // TMA stores of X and of the next operand).  Chosen by launch_gemm_tc when every tile is interior; never requested
+  // by callers.
+  TC_EPI_GATED_RESIDUAL_TMA = 8,
 };
 
 struct TcGemmArgs {
