@@ -295,7 +295,15 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
     if (EPI == TC_EPI_GATED_RESIDUAL) {
       if (!(a.experiment & 1)) {
 #pragma unroll
-      for (int ps = 0; ps < LPR; ++ps) xpre[ps] = *reinterpret_cast<const float4*>(xptr + ps * xpass + c * CW);
+      for (int ps = 0; ps < LPR; ++ps) {
+        if (a.experiment & 8) {   // experiment: residual loads that do not allocate L1 lines
+          const float* p = xptr + ps * xpass + c * CW;
+          asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(xpre[ps].x), "=f"(xpre[ps].y), "=f"(xpre[ps].z), "=f"(xpre[ps].w) : "l"(p) : "memory");
+        } else {
+          xpre[ps] = *reinterpret_cast<const float4*>(xptr + ps * xpass + c * CW);
+        }
+      }
       }
       g_n = *reinterpret_cast<const float4*>(modrow + a.gate_off + colv);
       if (a.nx_w) {
@@ -1490,6 +1498,15 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
   const int fixed = epi_bytes + (int)sizeof(TcSmemBars) + 1024 + rope_bytes;
   int nstages = (227 * 1024 - fixed) / stage_bytes;
   if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
+  {
+    static int cap = -1;   // VAVAE_GEMM_MAX_STAGES: developer experiment (how much does a shallower operand pipeline cost?)
+    if (cap < 0) { const char* e = std::getenv("VAVAE_GEMM_MAX_STAGES"); cap = e ? std::atoi(e) : 0; }
+    if (cap >= 2 && nstages > cap) nstages = cap;
+    static int pcap = -1;  // VAVAE_GEMM_PROJ_STAGES: same, attn.proj-shaped gated-residual launches only (K <= N)
+    if (pcap < 0) { const char* e = std::getenv("VAVAE_GEMM_PROJ_STAGES"); pcap = e ? std::atoi(e) : 0; }
+    if (pcap >= 2 && nstages > pcap && a.K <= a.N &&
+        (EPI == TC_EPI_GATED_RESIDUAL || EPI == TC_EPI_GATED_RESIDUAL_TMA)) nstages = pcap;
+  }
   VV_CHECK(nstages >= 2, "gemm_tc: tile too large for shared memory");
   const size_t smem = (size_t)nstages * stage_bytes + fixed;
   static std::atomic<uint64_t> attr_devices{0};   // one bit per device, per kernel instantiation
