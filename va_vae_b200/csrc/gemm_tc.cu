@@ -616,18 +616,24 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
 }
 
 // ------------------------------------------------------------------------------------------------ TMA epilogue
-// Gated residual with the residual stream moved by TMA (TC_EPI_GATED_RESIDUAL_TMA).  Per epilogue warp: a ring of two
-// 32 x 32 fp32 tiles (4 KB, 128-byte swizzle).  The tile of the NEXT chunk is in flight while the current one is
-// processed; the update happens in place in the thread == row domain (lane = accumulator row = tile row; the swizzle
-// makes 16-byte accesses of 32 different rows conflict-free), then one elected lane stores the tile - and the bf16
-// operand tile of the next GEMM - with cp.async.bulk.tensor.  Nothing of the residual stream goes through the LSU / L1
-// miss path, whose limited outstanding-miss capacity capped the register-prefetch epilogue at ~4 TB/s.
+// Gated residual with the residual stream moved by TMA (TC_EPI_GATED_RESIDUAL_TMA).  `xt_warps` epilogue warps - eight
+// (two per TMEM lane quarter, alternate column chunks) where the epilogue dominates, four (one per quarter, the others
+// retire at once; the shared memory saved keeps the fifth operand stage) where the main loop does - each with a ring of
+// `xt_slots` 32 x 32 fp32 tiles (4 KB, 128-byte swizzle).  The tiles of the next chunks are in flight while the current one is processed; the update happens in
+// place in the thread == row domain (lane = accumulator row = tile row; the swizzle makes 16-byte accesses of 32
+// different rows conflict-free), then one elected lane stores the tile - and the bf16 operand tile of the next GEMM -
+// with cp.async.bulk.tensor.  Nothing of the residual stream goes through the LSU / L1 miss path, whose limited
+// outstanding-miss capacity (what the shared-memory carve-out leaves of L1) capped the register-prefetch epilogue.
 // Same arithmetic as the other two paths: x' = fma(gate, acc + bias, x); operand = bf16(x' * w * (1 + scale));
 // partial sums of x'^2 in the same grouping and order (sumsq4 per 4 columns, 8 column groups combined as a butterfly).
 constexpr int XT_BYTES = 32 * 128;         // residual tile
 constexpr int NXT_BYTES = 32 * 64;         // bf16 operand tile
-constexpr int VEC_BYTES = 4 * 3 * 128;     // per warp: [4 chunks][bias | gate | w*(1+scale)][32 columns]
-constexpr int TMA_EPI_BYTES = 8 * (2 * XT_BYTES + NXT_BYTES + VEC_BYTES);
+constexpr int VEC_BYTES = 3 * 128;         // per chunk: [bias | gate | w*(1+scale)][32 columns]
+constexpr int XT_MAX_SLOTS = 4;
+// `warps` epilogue warps (4: one per TMEM lane quarter, every chunk; 8: two per quarter, alternate chunks)
+__host__ __device__ constexpr int tma_epi_bytes(int slots, int warps) {
+  return warps * (slots * XT_BYTES + NXT_BYTES + (32 / warps) * VEC_BYTES);
+}
 
 // (the residual / operand tensor maps are encoded with rank 4 - make_tmap_4d - so the 4-D instruction forms are used)
 __device__ __forceinline__ void tma_load_tile(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
@@ -647,7 +653,7 @@ struct TcSmemBars {
   uint64_t empty[TC_MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
-  uint64_t xfull[8][2];   // TMA epilogue: residual-tile ring, [epilogue warp][slot]
+  uint64_t xfull[8][XT_MAX_SLOTS];   // TMA epilogue: residual-tile ring, [epilogue warp][slot]
   uint32_t tmem_base;
 };
 
@@ -745,7 +751,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int sched_n = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   float* staging = reinterpret_cast<float*>(smem + (size_t)nstages * stage_bytes);
   TcSmemBars* bars = reinterpret_cast<TcSmemBars*>(
-      reinterpret_cast<uint8_t*>(staging) + (EPI == TC_EPI_GATED_RESIDUAL_TMA ? TMA_EPI_BYTES : 8 * 32 * (CW + 4) * 4));
+      reinterpret_cast<uint8_t*>(staging) + (EPI == TC_EPI_GATED_RESIDUAL_TMA ? tma_epi_bytes(a.xt_slots, a.xt_warps) : 8 * 32 * (CW + 4) * 4));
   // QKV: compact RoPE tables (a few KB of constants) live in shared memory for the whole kernel
   float* rope_tab_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~(uintptr_t)15);
   const bool rope_smem = EPI == TC_EPI_QKV && a.rope_tab != nullptr;
@@ -772,15 +778,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->tfull[i], 1);
-      ptx::mbar_init(&bars->tempty[i], TWO ? 512 : 256);   // 2-CTA: both CTAs' epilogue threads release the leader
+      // 2-CTA: both CTAs' epilogue threads release the leader; the TMA epilogue may run on four of the eight warps
+      ptx::mbar_init(&bars->tempty[i], (TWO ? 2 : 1) * 32 * (EPI == TC_EPI_GATED_RESIDUAL_TMA ? a.xt_warps : 8));
     }
     if (EPI == TC_EPI_GATED_RESIDUAL_TMA) {
       ptx::prefetch_tmap(&tmX);
       ptx::prefetch_tmap(&tmNX);
-      for (int i = 0; i < 8; ++i) {
-        ptx::mbar_init(&bars->xfull[i][0], 1);
-        ptx::mbar_init(&bars->xfull[i][1], 1);
-      }
+      for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < XT_MAX_SLOTS; ++j) ptx::mbar_init(&bars->xfull[i][j], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -913,14 +918,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     };
     if (EPI == TC_EPI_GATED_RESIDUAL_TMA) {
       // every tile is interior and the warp's 32 rows belong to one sample (launch_gemm_tc checked it)
-      const int ew = warp - 2;
+      const int NH = a.xt_warps >> 2;   // warps per TMEM lane quarter (1 or 2); warp `half` takes chunks half, half + NH, ...
+      if (half < NH) {
+      const int NS = a.xt_slots, ew = half * 4 + q, NW = a.xt_warps;
       const uint32_t epi_s = ptx::smem_u32(staging);
-      const uint32_t xs = epi_s + (uint32_t)ew * (2 * XT_BYTES);
-      const uint32_t nxs = epi_s + 8 * 2 * XT_BYTES + (uint32_t)ew * NXT_BYTES;
-      const uint32_t vs = epi_s + 8 * (2 * XT_BYTES + NXT_BYTES) + (uint32_t)ew * VEC_BYTES;
+      const uint32_t xs = epi_s + (uint32_t)(ew * NS) * XT_BYTES;
+      const uint32_t nxs = epi_s + (uint32_t)(NW * NS) * XT_BYTES + (uint32_t)ew * NXT_BYTES;
+      const uint32_t vs = epi_s + (uint32_t)(NW * NS) * XT_BYTES + (uint32_t)NW * NXT_BYTES + (uint32_t)(ew * (32 / NW)) * VEC_BYTES;
       uint64_t* xbar = bars->xfull[ew];
       const bool has_nx = a.nx_w != nullptr;
-      // this warp's (tile, chunk) stream; `ld_*` runs two positions ahead of the chunk being processed
+      // this warp's (tile, chunk) stream; `ld_*` runs NS positions ahead of the chunk being processed
       int ld_tile = sched_id, ld_c = half;
       auto ld_issue = [&](int slot) {   // lane 0 only
         if (ld_tile >= num_tiles) return;
@@ -929,11 +936,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::mbar_expect_tx(&xbar[slot], XT_BYTES);
         tma_load_tile(xs + (uint32_t)slot * XT_BYTES, &tmX, ptx::smem_u32(&xbar[slot]), col0, row0);
         const int nch = ((nb == n_tiles - 1) ? BNlast : BN) >> 5;
-        ld_c += 2;
+        ld_c += NH;
         if (ld_c >= nch) { ld_tile += sched_n; ld_c = half; }
       };
-      if (lane == 0) { ld_issue(0); ld_issue(1); }
-      uint32_t k = 0;   // position in the stream
+      if (lane == 0)
+        for (int i = 0; i < NS; ++i) ld_issue(i);
+      uint32_t slot = 0, sphase = 0;   // ring position of the chunk being processed
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
         const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
@@ -941,17 +949,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int wrow0 = m0 + q * 32;
         const int wb = wrow0 / a.T;
         const float* modrow = a.mod + (size_t)wb * a.mod_ld;
-        // per-column vectors of this warp's chunks (lane = column): bias, gate, and the next norm's w * (1 + scale)
+        // per-column vectors of the tile (lane = column): bias, gate, and the next norm's w * (1 + scale)
         __syncwarp();
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = half + 2 * ci;
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c = half + ci * NH;
           if (c < n_chunks) {
             const int col = n0 + c * 32 + lane;
             const float bv = a.bias ? a.bias[col] : 0.f;
             const float gv = modrow[a.gate_off + col];
             const float cv = has_nx ? a.nx_w[col] * (1.f + modrow[a.nx_scale_off + col]) : 0.f;
-            const uint32_t vb = vs + (uint32_t)(ci * 3) * 128 + (uint32_t)lane * 4;
+            const uint32_t vb = vs + (uint32_t)ci * VEC_BYTES + (uint32_t)lane * 4;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb), "f"(bv) : "memory");
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 128), "f"(gv) : "memory");
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 256), "f"(cv) : "memory");
@@ -961,22 +969,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::mbar_wait(&bars->tfull[as], aphase);
         ptx::tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
-        float ss[8];
+        float ss[2][8];   // partial sums of the even / odd chunks (the slot grouping of the eight-warp epilogues)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss[i] = 0.f;
-#pragma unroll 1
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = half + 2 * ci;
+        for (int i = 0; i < 8; ++i) ss[0][i] = ss[1][i] = 0.f;
+#pragma unroll 2
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c = half + ci * NH;
           if (c >= n_chunks) break;
-          const uint32_t slot = k & 1u;
           const uint32_t xt = xs + slot * XT_BYTES + (uint32_t)lane * 128;
           uint32_t r[32];
           ptx::tmem_ld_x32(tbase + (uint32_t)(c * 32), r);
-          ptx::mbar_wait(&xbar[slot], (k >> 1) & 1u);   // the residual tile of this chunk has landed
+          ptx::mbar_wait(&xbar[slot], sphase);          // the residual tile of this chunk has landed
           ptx::tmem_ld_wait();
-          if (c + 2 >= n_chunks) release_acc(as);       // last read of this accumulator stage by this warp
+          if (c + NH >= n_chunks) release_acc(as);      // last read of this accumulator stage by this warp
           uint32_t nxw[16];
-          const uint32_t vb = vs + (uint32_t)(ci * 3) * 128;
+          const uint32_t vb = vs + (uint32_t)ci * VEC_BYTES;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const uint32_t xa = xt + (uint32_t)((j4 ^ (lane & 7)) << 4);
@@ -989,7 +996,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             sts128(xa, x.x, x.y, x.z, x.w);
             if (has_nx) {
               const float4 c4 = lds128(vb + 256 + j4 * 16);
-              ss[j4] += sumsq4(x);
+              if (c & 1) ss[1][j4] += sumsq4(x); else ss[0][j4] += sumsq4(x);
               nxw[j4 * 2] = pack_bf16(x.x * c4.x, x.y * c4.y);
               nxw[j4 * 2 + 1] = pack_bf16(x.z * c4.z, x.w * c4.w);
             }
@@ -1009,20 +1016,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tma_store_tile(&tmX, xs + slot * XT_BYTES, col0, wrow0);
             if (has_nx) tma_store_tile(&tmNX, nxs, col0, wrow0);
             ptx::tma_store_commit();
-            ptx::tma_store_wait_read0();   // both source tiles have been read: the slot takes the load two chunks ahead
+            ptx::tma_store_wait_read0();   // both source tiles have been read: the slot takes the load NS chunks ahead
             ld_issue((int)slot);
           }
           __syncwarp();                    // no lane rewrites the operand tile before the store has read it
-          ++k;
+          if (++slot == (uint32_t)NS) { slot = 0; sphase ^= 1u; }
         }
         if (has_nx) {
-          const float v = ((ss[0] + ss[4]) + (ss[2] + ss[6])) + ((ss[1] + ss[5]) + (ss[3] + ss[7]));
-          a.nx_part[(size_t)(wrow0 + lane) * 32 + (n_blk * 2 + half)] = v;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h < n_chunks && (NH == 1 || h == half)) {
+              const float v = ((ss[h][0] + ss[h][4]) + (ss[h][2] + ss[h][6])) + ((ss[h][1] + ss[h][5]) + (ss[h][3] + ss[h][7]));
+              a.nx_part[(size_t)(wrow0 + lane) * 32 + (n_blk * 2 + h)] = v;
+            }
+          }
         }
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
       if (lane == 0) ptx::tma_store_wait_all();
+      }
     } else
     for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
       const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
@@ -1494,7 +1507,7 @@ static void launch_inst2(const TcGemmArgs& a, int BN, cudaStream_t s) {
   const int b_rows = TWO ? BN / 2 : BN;
   const int stage_bytes = TC_A_BYTES + b_rows * 128;
   const int rope_bytes = (EPI == TC_EPI_QKV && a.rope_tab) ? 2 * a.rope_gw * (a.hd / 4) * 8 + 16 : 0;
-  const int epi_bytes = EPI == TC_EPI_GATED_RESIDUAL_TMA ? TMA_EPI_BYTES : 8 * 32 * (CW + 4) * 4;
+  const int epi_bytes = EPI == TC_EPI_GATED_RESIDUAL_TMA ? tma_epi_bytes(a.xt_slots, a.xt_warps) : 8 * 32 * (CW + 4) * 4;
   const int fixed = epi_bytes + (int)sizeof(TcSmemBars) + 1024 + rope_bytes;
   int nstages = (227 * 1024 - fixed) / stage_bytes;
   if (nstages > TC_MAX_STAGES) nstages = TC_MAX_STAGES;
@@ -1627,14 +1640,20 @@ void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
       static int tma_epi = -1;
       if (tma_epi < 0) { const char* e = std::getenv("VAVAE_GEMM_TMA_EPI"); tma_epi = e ? std::atoi(e) : 2; }
       const int BNl = gemm_tc_last_bn(a, BN);
-      // 1: every eligible launch; 2 (default): only where the epilogue dominates (K <= N, attn.proj) - the TMA variant gives
-      // up one or two operand stages for its ring, which costs the main-loop-bound mlp.w3 more than its epilogue gains
-      const bool tma_ok = tma_epi && (tma_epi == 1 || a.K <= a.N) && exp_mode == 0 && cw == 32 && a.T > 0 && a.T % 32 == 0 && a.M % (2 * TC_BM) == 0 &&
+      // 1: every eligible launch;
+      // 2 (default): where it measured faster - attn.proj (K <= N: epilogue-bound, eight epilogue warps) and the long-K
+      // mlp.w3 of the XL model (main-loop-bound: four epilogue warps, all five operand stages kept)
+      const bool tma_ok = tma_epi && (tma_epi == 1 || a.K <= a.N || a.K >= 3072) && exp_mode == 0 && BN <= 256 && cw == 32 && a.T > 0 && a.T % 32 == 0 && a.M % (2 * TC_BM) == 0 &&
                           BN % 32 == 0 && BNl % 32 == 0 && (a.N % BN == 0 || a.N % BN == BNl) && a.ldo % 8 == 0 &&
                           a.N <= a.ldo && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
                           (!a.nx_w || (reinterpret_cast<uintptr_t>(a.nx_A) & 15) == 0) && a.mod != nullptr;
       if (tma_ok) {
         b.epi = TC_EPI_GATED_RESIDUAL_TMA;
+        // ring depth per epilogue warp (VAVAE_GEMM_XT_SLOTS: developer knob)
+        static int xt_env = -1;
+        if (xt_env < 0) { const char* e = std::getenv("VAVAE_GEMM_XT_SLOTS"); xt_env = e ? std::atoi(e) : 0; }
+        b.xt_slots = (xt_env >= 2 && xt_env <= XT_MAX_SLOTS) ? xt_env : 2;
+        b.xt_warps = a.K <= a.N ? 8 : 4;
         launch_epi<TC_EPI_GATED_RESIDUAL_TMA>(b, BN, cw, s);
       } else {
         launch_epi<TC_EPI_GATED_RESIDUAL>(b, BN, cw, s);

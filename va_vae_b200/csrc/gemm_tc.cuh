@@ -85,6 +85,9 @@ struct TcGemmArgs {
   // next so that a consumer starts on the rows its producer wrote LAST - the part of a larger-than-L2 tensor that is
   // still cached.  Results do not depend on it (no atomics, fixed partial-sum slots).
   int reverse_m;
+  // TC_EPI_GATED_RESIDUAL_TMA only (set by launch_gemm_tc): residual tiles per epilogue warp in the shared-memory ring
+  int xt_slots;
+  int xt_warps;   // 4 or 8 epilogue warps
 };
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
