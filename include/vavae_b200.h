@@ -165,7 +165,12 @@ int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void
  *   VAVAE_EPI_GATED_RESIDUAL attn.proj / mlp.w3: X += gate[b] * (acc + bias) (models/lightningdit.py:248-249), optionally
  *                            emitting the next RMSNorm's un-normalised bf16 operand and per-row partial sums of squares
  * Optional consumer-side fused RMSNorm (kinds QKV, SWIGLU): accumulator rows are scaled by
- * rsqrt(sum(in_part[row, :in_nparts]) / in_dim + 1e-6) and sp[row / T, :] replaces the bias. */
+ * rsqrt(total / in_dim + 1e-6) and sp[row / T, :] replaces the bias.  Partial sums come in two layouts (rows part_ld
+ * floats apart): COARSE, one float per 128-column group, summed in ascending order (in_nparts of them); or FINE
+ * (in_fine = 1), eight floats per 32-column chunk (sums of squares of 4 columns each; in_nparts chunks), which the
+ * consumer folds into exactly the coarse values first.  A producer (GATED_RESIDUAL with nx_w) reports which layout it
+ * wrote in fine_out (wide tiles: coarse; narrow tiles of small-M launches: fine) and how many slots / chunks in
+ * nparts_out. */
 #define VAVAE_EPI_QKV 0
 #define VAVAE_EPI_SWIGLU 1
 #define VAVAE_EPI_GATED_RESIDUAL 2
@@ -175,7 +180,7 @@ typedef struct vavae_epilogue_test {
   const void* A;            /* bf16 [M, K] */
   const void* W;            /* bf16 [N, K]; SWIGLU: rows interleaved (x1_j, x2_j) */
   const float* bias;        /* [N] (SWIGLU: interleaved like W) */
-  const float* in_part;     /* optional f32 [M, 32] partial sums of squares */
+  const float* in_part;     /* optional f32 [M, part_ld] partial sums of squares */
   int32_t in_nparts, in_dim;
   const float* sp;          /* f32 [M / T, sp_ld] per-sample shift.W^T + bias vectors (with in_part) */
   int32_t sp_ld;
@@ -195,8 +200,11 @@ typedef struct vavae_epilogue_test {
   const float* nx_w;        /* optional f32 [N]: weight of the RMSNorm that follows */
   int32_t nx_scale_off;     /* column of its adaLN scale in mod */
   void* nx_A;               /* bf16 [M, N]: x_new * nx_w * (1 + scale) */
-  float* nx_part;           /* f32 [M, 32]: partial sums of x_new^2, nparts_out slots used */
+  float* nx_part;           /* f32 [M, part_ld]: partial sums of x_new^2 (part_ld >= 16 coarse, >= N / 4 fine) */
   int32_t nparts_out;       /* written by the call */
+  int32_t in_fine;          /* consumer: in_part holds fine (32-column) slots */
+  int32_t fine_out;         /* written by the call: the producer wrote fine slots */
+  int32_t part_ld;          /* row pitch (floats) of in_part / nx_part */
 } vavae_epilogue_test_t;
 int vavae_test_gemm_epilogue(vavae_epilogue_test_t* t, void* stream);
 

@@ -89,11 +89,11 @@ def test_swiglu_epilogue(fused_norm, S):
     kw = {}
     if fused_norm:
         # producer contract: A = un-normalised x * w * (1 + scale), partial sums of x^2 in 5 slots, per-sample vector sp
-        part = torch.zeros(M, 32)
+        part = torch.zeros(M, 16)
         part[:, :5] = _rand(M, 5, seed=7).abs() * K / 5
         rstd = torch.rsqrt(part.sum(1) / K + 1e-6)
         bias_rows = _rand(Bn, 2 * S, seed=8, scale=0.2)
-        kw = dict(in_part=part.to(dev), in_nparts=5, in_dim=K, sp_ld=N)
+        kw = dict(in_part=part.to(dev), in_nparts=5, in_dim=K, sp_ld=N, part_ld=16)
     U = (ref_in @ W12.float().t()) * rstd[:, None] + bias_rows.repeat_interleave(T, 0)
     want = torch.nn.functional.silu(U[:, :S]) * U[:, S:]                               # swiglu_ffn.py:33-35
     # engine layout: rows (x1_j, x2_j) interleaved, N padded to a multiple of 4 with zero rows
@@ -135,8 +135,9 @@ def test_gated_residual_epilogue(N, K, next_norm, T, Bn):
     if next_norm:
         nx_w = 1 + 0.1 * _rand(N, seed=3)
         nxA = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
-        part = torch.full((M, 32), float("nan"), device=dev)
-        kw = dict(nx_w=nx_w.to(dev), nx_scale_off=scale_off, nx_A=nxA, nx_part=part)
+        PL = max(16, N // 4)
+        part = torch.full((M, PL), float("nan"), device=dev)
+        kw = dict(nx_w=nx_w.to(dev), nx_scale_off=scale_off, nx_A=nxA, nx_part=part, part_ld=PL)
     nparts = E.test_gemm_epilogue(kind=E.EPI_GATED_RESIDUAL, M=M, N=N, K=K, T=T, A=A.to(dev), W=W.to(dev),
                                   bias=bias.to(dev), X=X, mod=mod.to(dev), mod_ld=mod_ld, gate_off=gate_off, **kw)
     torch.cuda.synchronize()
@@ -144,12 +145,93 @@ def test_gated_residual_epilogue(N, K, next_norm, T, Bn):
     if next_norm:
         scale = mod[:, scale_off: scale_off + N].repeat_interleave(T, 0)
         assert rel_l2(nxA, want * nx_w * (1 + scale)) < 3e-3                           # un-normalised operand of the next GEMM
-        assert 0 < nparts <= 32 and not torch.isnan(part[:, :nparts]).any()
+        fine = E.test_gemm_epilogue.fine_out
+        # 384 = 256 + 128, 1152 = 4 x 256 + 128, 768 = 3 x 256: every tile holds whole 128-column groups -> coarse slots
+        assert fine == 0 and nparts == (N + 127) // 128
+        assert not torch.isnan(part[:, :nparts]).any()
         assert rel_l2(part[:, :nparts].sum(1), (want * want).sum(1)) < 1e-5            # what the consumer turns into 1/rms
         assert torch.isnan(part[:, nparts:]).all()                                     # no slot beyond nparts is touched
         # the slots are a pure function of the row: a second launch on the same inputs is bit-identical
-        X2, part2 = X0.clone().to(dev), torch.zeros(M, 32, device=dev)
+        X2, part2 = X0.clone().to(dev), torch.zeros(M, PL, device=dev)
         kw2 = dict(kw, nx_part=part2, nx_A=torch.zeros_like(nxA))
         E.test_gemm_epilogue(kind=E.EPI_GATED_RESIDUAL, M=M, N=N, K=K, T=T, A=A.to(dev), W=W.to(dev), bias=bias.to(dev),
                              X=X2, mod=mod.to(dev), mod_ld=mod_ld, gate_off=gate_off, **kw2)
         assert torch.equal(part2[:, :nparts], part[:, :nparts]) and torch.equal(X2, X)
+
+
+def _fold_fine(fine, nchunks):
+    """Coarse (128-column) slots from fine ones ([M, nchunks * 8]: s(c, j) = sum of squares of columns 32c + 4j .. + 3)
+    in the kernels' order: fold8_j( ((s(4g, j) + s(4g+1, j)) + s(4g+2, j)) + s(4g+3, j) )."""
+    ng = (nchunks + 3) // 4
+    out = torch.zeros(fine.shape[0], ng, dtype=torch.float32, device=fine.device)
+    s = fine[:, : nchunks * 8].reshape(fine.shape[0], nchunks, 8)
+    for g in range(ng):
+        t = s[:, 4 * g].clone()
+        for c in range(4 * g + 1, min(4 * g + 4, nchunks)):
+            t = t + s[:, c]
+        out[:, g] = ((t[:, 0] + t[:, 4]) + (t[:, 2] + t[:, 6])) + ((t[:, 1] + t[:, 5]) + (t[:, 3] + t[:, 7]))
+    return out
+
+
+@pytest.mark.parametrize("N,K", [(384, 384), (1152, 3072), (1152, 1152), (96, 384)])
+def test_gated_residual_paths_agree_bitwise(N, K):
+    """The same rows through the TMA epilogue (M = 768: whole 256-row tile pairs) and through the register-prefetch /
+    guarded epilogues (M = 480): residual stream, next operand and partial sums must be bit-identical, or results would
+    depend on the batch size.  N = 96 is one narrow tile: fine slots on both paths."""
+    from va_vae_b200 import engine as E
+    dev = _dev()
+    T = 32
+    PL = max(16, N // 4)
+    res = {}
+    for M in (768, 480):
+        Bn = M // T
+        A, W, bias = _operands(768, N, K, seed=91)
+        X0 = _rand(768, N, seed=5)
+        mod_ld, gate_off, scale_off = 3 * N + 8, 8, 8 + 2 * N
+        mod = _rand(768 // T, mod_ld, seed=6, scale=0.5)
+        nx_w = 1 + 0.1 * _rand(N, seed=3)
+        X = X0[:M].clone().to(dev)
+        nxA = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+        part = torch.zeros(M, PL, device=dev)
+        nparts = E.test_gemm_epilogue(kind=E.EPI_GATED_RESIDUAL, M=M, N=N, K=K, T=T, A=A[:M].contiguous().to(dev),
+                                      W=W.to(dev), bias=bias.to(dev), X=X, mod=mod[:Bn].contiguous().to(dev), mod_ld=mod_ld,
+                                      gate_off=gate_off, nx_w=nx_w.to(dev), nx_scale_off=scale_off, nx_A=nxA, nx_part=part,
+                                      part_ld=PL)
+        torch.cuda.synchronize()
+        res[M] = (X, nxA, part, nparts, E.test_gemm_epilogue.fine_out)
+    (Xa, Na, Pa, na, fa), (Xb, Nb, Pb, nb, fb) = res[768], res[480]
+    assert fa == fb == (1 if N % 128 else 0) and na == nb == (N // 32 if fa else (N + 127) // 128)
+    assert torch.equal(Xa[:480], Xb) and torch.equal(Na[:480], Nb)
+    width = na * 8 if fa else na
+    assert torch.equal(Pa[:480, :width], Pb[:, :width])
+    want_ss = (Xb.double() ** 2).sum(1)
+    got = _fold_fine(Pb, nb).sum(1) if fb else Pb[:, :nb].sum(1)
+    assert rel_l2(got.double(), want_ss) < 1e-5
+
+
+def test_fused_norm_consumer_fine_and_coarse_slots_agree_bitwise():
+    """A consumer (mlp.w12 here) fed fine slots folds them into the groups a coarse-slot producer would have written."""
+    from va_vae_b200 import engine as E
+    dev = _dev()
+    T, Bn, K, S = 256, 3, 384, 512
+    M, N = Bn * T, 2 * S
+    A, W12, b12 = _operands(M, N, K, seed=33)
+    nch, ng = K // 32, (K + 127) // 128
+    fine = _rand(M, nch * 8, seed=7).abs() * 4
+    coarse = _fold_fine(fine, nch)
+    sp = _rand(Bn, N, seed=8, scale=0.2)
+    outs = []
+    for part, nparts, is_fine, pl in ((fine, nch, 1, nch * 8 + 8), (coarse, ng, 0, 16)):
+        out = torch.zeros(M, S, dtype=torch.bfloat16, device=dev)
+        p = torch.full((M, pl), 1e30)                      # stale values behind the valid slots must be ignored
+        p[:, : part.shape[1]] = part
+        E.test_gemm_epilogue(kind=E.EPI_SWIGLU, M=M, N=N, K=K, T=T, A=A.to(dev), W=W12.to(dev), bias=b12.to(dev),
+                             out_bf16=out, ldo=S, in_part=p.to(dev), in_nparts=nparts, in_fine=is_fine, in_dim=K,
+                             sp=sp.to(dev), sp_ld=N, part_ld=pl)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    rstd = torch.rsqrt(coarse.sum(1) / K + 1e-6)
+    U = (A.float() @ W12.float().t()) * rstd[:, None] + sp.repeat_interleave(T, 0)
+    want = torch.nn.functional.silu(U[:, 0::2]) * U[:, 1::2]
+    assert rel_l2(outs[0], want) < 3e-3

@@ -38,7 +38,8 @@ struct vavae_engine {
   int NMx = 0;      // row pitch of `mod`: NM modulation columns + (fused norm) per-layer shift.W^T+bias columns
   int N1 = 0;       // output columns of the first MLP GEMM (2S rounded to 4 for SwiGLU, S for GELU)
   bool fuse = false;  // RMSNorm+modulate folded into the producing / consuming GEMM epilogues
-  float *part1 = nullptr, *part2 = nullptr;  // per-row partial sums of squares [n_parts, M]
+  float *part1 = nullptr, *part2 = nullptr;  // per-row partial sums of squares (TcGemmArgs::nx_part), part_floats each
+  size_t part_floats = 0;
   bool fp32;
   bool finalized = false;
   int chunk_rows = 0;
@@ -497,8 +498,12 @@ static void finalize(vavae_engine* e, cudaStream_t s) {
     e->A3_h = e->alloc<bf16>(M * 3 * D);
     e->Aemb_h = e->alloc<bf16>(M * 3 * e->C * e->p * e->p);
     if (e->fuse) {
-      e->part1 = e->alloc<float>(32 * M, true);
-      e->part2 = e->alloc<float>(32 * M, true);
+      // coarse slots: 16 floats per row at any M; fine slots (D / 4 floats per row) only arise on the narrow tiles of
+      // small-M launches - or at every M when D is not a multiple of 128 (no registry model)
+      const size_t fine_rows = (D % 128) ? (size_t)M : std::min<size_t>((size_t)M, 4096);
+      e->part_floats = std::max<size_t>((size_t)16 * M, fine_rows * (size_t)(D / 4));
+      e->part1 = e->alloc<float>(e->part_floats, true);
+      e->part2 = e->alloc<float>(e->part_floats, true);
     }
     // padding columns d in [hd, hdp) of q/k and rows [hd, hdv) of v^T stay zero forever (never written)
     e->q_h = e->alloc<bf16>((size_t)R * e->H * T * e->hdp, true);
@@ -628,7 +633,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
   const float* rcos = c.use_rope ? e->W("feat_rope.freqs_cos").d : nullptr;
   const float* rsin = c.use_rope ? e->W("feat_rope.freqs_sin").d : nullptr;
 
-  int np_proj = 0, np_w3 = 0;  // number of partial-sum slots the last proj / w3 epilogue wrote
+  int pc_proj = 0, pc_w3 = 0;  // kind of partial-sum slots (1 coarse / 0 fine) the last proj / w3 epilogue wrote
   for (int i = 0; i < L; ++i) {
     const ModOff mo = mod_offsets(e, i);
     const float* n1 = c.use_rmsnorm ? e->W(blk(i, "norm1.weight")).d : nullptr;
@@ -672,7 +677,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       a.q = e->q_h; a.k = e->k_h; a.vt = e->vt_h; a.cos = rcos; a.sin = rsin; a.rope_cs = e->rope_cs; a.rope_tab = e->rope_tab; a.rope_gw = e->rope_gw; a.qn_w = qnw; a.qn_b = qnb; a.kn_w = knw;
       a.kn_b = knb; a.qk_rms = c.use_rmsnorm; a.H = H; a.hd = hd; a.hdp = e->hdp; a.hdv = e->hdv; a.T = T;
       if (fuse && i > 0) {
-        a.in_part = e->part2; a.in_nparts = np_w3; a.in_dim = D;
+        a.in_part = e->part2; a.in_fine = !pc_w3; a.in_nslots = gemm_tc_part_slots(D, pc_w3); a.in_part_ld = gemm_tc_part_ld(D, pc_w3); a.in_dim = D;
         a.sp = sp_qkv ? sp_qkv : bqkv; a.sp_ld = sp_qkv ? e->NMx : 0;
       }
       {
@@ -692,7 +697,9 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NMx; pr.gate_off = mo.gate_msa; pr.T = T;
       if (fuse) {  // emit the operand of this block's MLP norm (norm2)
         pr.nx_w = n2; pr.nx_scale_off = mo.scale_mlp; pr.nx_A = e->A_h; pr.nx_part = e->part1;
-        np_proj = 2 * cdiv(D, gemm_tc_pick_bn(pr));
+        pc_proj = gemm_tc_part_coarse(pr);
+        pr.nx_part_ld = gemm_tc_part_ld(D, pc_proj);
+        VV_CHECK((size_t)M * pr.nx_part_ld <= e->part_floats, "partial-sum buffer too small for this batch");
       }
       {
         ProfScope ps(e, PK_PROJ, 2.0 * M * (double)D * D, s);
@@ -725,7 +732,7 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
                                e->lw[i].b1);
         a.out = e->Hh_h; a.ldo = e->Spad; a.T = T;
         if (fuse) {
-          a.in_part = e->part1; a.in_nparts = np_proj; a.in_dim = D;
+          a.in_part = e->part1; a.in_fine = !pc_proj; a.in_nslots = gemm_tc_part_slots(D, pc_proj); a.in_part_ld = gemm_tc_part_ld(D, pc_proj); a.in_dim = D;
           a.sp = sp_mlp ? sp_mlp : e->lw[i].b1; a.sp_ld = sp_mlp ? e->NMx : 0;
         }
         ProfScope ps(e, PK_W12, 2.0 * M * (c.use_swiglu ? 2.0 : 1.0) * S * D, s);
@@ -738,7 +745,9 @@ static void forward_chunk(vavae_engine* e, int rows, const RowMap& rm, const flo
       if (fuse && i + 1 < L) {  // emit the operand of the next block's attention norm (norm1)
         const ModOff nmo = mod_offsets(e, i + 1);
         a.nx_w = e->W(blk(i + 1, "norm1.weight")).d; a.nx_scale_off = nmo.scale_msa; a.nx_A = e->A_h; a.nx_part = e->part2;
-        np_w3 = 2 * cdiv(D, gemm_tc_pick_bn(a));
+        pc_w3 = gemm_tc_part_coarse(a);
+        a.nx_part_ld = gemm_tc_part_ld(D, pc_w3);
+        VV_CHECK((size_t)M * a.nx_part_ld <= e->part_floats, "partial-sum buffer too small for this batch");
       }
       {
         ProfScope ps(e, PK_W3, 2.0 * M * (double)S * D, s);
@@ -1355,7 +1364,7 @@ int vavae_test_gemm_epilogue(vavae_epilogue_test_t* t, void* stream) {
     a.T = t->T;
     if (t->in_part) {
       VV_CHECK(t->kind != VAVAE_EPI_GATED_RESIDUAL && t->sp, "test_gemm_epilogue: fused-norm consumer needs sp and kind 0/1");
-      a.in_part = t->in_part; a.in_nparts = t->in_nparts; a.in_dim = t->in_dim; a.sp = t->sp; a.sp_ld = t->sp_ld;
+      a.in_part = t->in_part; a.in_nslots = t->in_nparts; a.in_fine = t->in_fine; a.in_part_ld = t->part_ld; a.in_dim = t->in_dim; a.sp = t->sp; a.sp_ld = t->sp_ld;
     }
     if (t->kind == VAVAE_EPI_QKV) {
       VV_CHECK(t->q && t->k && t->vt && t->H > 0 && t->hd > 0 && t->N == 3 * t->H * t->hd, "test_gemm_epilogue: qkv outputs");
@@ -1390,7 +1399,10 @@ int vavae_test_gemm_epilogue(vavae_epilogue_test_t* t, void* stream) {
       if (t->nx_w) {
         VV_CHECK(t->nx_A && t->nx_part, "test_gemm_epilogue: next-norm outputs");
         a.nx_w = t->nx_w; a.nx_scale_off = t->nx_scale_off; a.nx_A = (bf16*)t->nx_A; a.nx_part = t->nx_part;
-        t->nparts_out = 2 * cdiv(t->N, gemm_tc_pick_bn(a));
+        t->fine_out = !gemm_tc_part_coarse(a);
+        t->nparts_out = gemm_tc_part_slots(t->N, !t->fine_out);
+        a.nx_part_ld = t->part_ld;
+        VV_CHECK(t->part_ld >= gemm_tc_part_ld(t->N, !t->fine_out), "test_gemm_epilogue: part_ld too small");
       }
     }
     launch_gemm_tc(a, s);
@@ -1452,7 +1464,9 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
       if (c.use_qknorm) { a.qn_w = e->W(blk(0, "attn.q_norm.weight")).d; a.kn_w = e->W(blk(0, "attn.k_norm.weight")).d; }
       if (fused) {   // as launched for layers >= 1: 1/rms from the previous w3's partial sums, per-sample sp vector
         TcGemmArgs w3 = tc_args(e->Hh_h, e->Spad, e->lw[0].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL, nullptr);
-        a.in_part = e->part2; a.in_nparts = 2 * cdiv(D, gemm_tc_pick_bn(w3)); a.in_dim = D;
+        w3.out = e->X; w3.ldo = D; w3.mod = e->mod; w3.T = T; w3.nx_w = e->W(blk(0, "norm1.weight")).d; w3.nx_A = e->A_h;
+        const int pc = gemm_tc_part_coarse(w3);
+        a.in_part = e->part2; a.in_fine = !pc; a.in_nslots = gemm_tc_part_slots(D, pc); a.in_part_ld = gemm_tc_part_ld(D, pc); a.in_dim = D;
         a.sp = sp0 ? sp0 : a.bias; a.sp_ld = sp0 ? e->NMx : 0;
       }
       launch_gemm_tc(a, s);
@@ -1462,7 +1476,10 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
     fn = [&] {
       TcGemmArgs pr = tc_args(e->O_h, D, e->lw[0].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, e->W(blk(0, "attn.proj.bias")).d);
       pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.mod_ld = e->NMx; pr.gate_off = mo.gate_msa; pr.T = T;
-      if (fused) { pr.nx_w = e->W(blk(0, "norm2.weight")).d; pr.nx_scale_off = mo.scale_mlp; pr.nx_A = e->A_h; pr.nx_part = e->part1; }
+      if (fused) {
+        pr.nx_w = e->W(blk(0, "norm2.weight")).d; pr.nx_scale_off = mo.scale_mlp; pr.nx_A = e->A_h; pr.nx_part = e->part1;
+        pr.nx_part_ld = gemm_tc_part_ld(D, gemm_tc_part_coarse(pr));
+      }
       launch_gemm_tc(pr, s);
     };
   } else if (k == "gemm_w12") {
@@ -1473,7 +1490,9 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
       a.out = e->Hh_h; a.ldo = e->Spad; a.T = T;
       if (fused) {
         TcGemmArgs pr = tc_args(e->O_h, D, e->lw[0].proj, D, M, D, D, TC_EPI_GATED_RESIDUAL, nullptr);
-        a.in_part = e->part1; a.in_nparts = 2 * cdiv(D, gemm_tc_pick_bn(pr)); a.in_dim = D;
+        pr.out = e->X; pr.ldo = D; pr.mod = e->mod; pr.T = T; pr.nx_w = e->W(blk(0, "norm2.weight")).d; pr.nx_A = e->A_h;
+        const int pc = gemm_tc_part_coarse(pr);
+        a.in_part = e->part1; a.in_fine = !pc; a.in_nslots = gemm_tc_part_slots(D, pc); a.in_part_ld = gemm_tc_part_ld(D, pc); a.in_dim = D;
         a.sp = sp0 ? sp0 + 3 * D : a.bias; a.sp_ld = sp0 ? e->NMx : 0;
       }
       launch_gemm_tc(a, s);
@@ -1484,7 +1503,10 @@ int vavae_time_kernel(vavae_engine_t* e, const char* kernel, int rows, int iters
       TcGemmArgs a = tc_args(e->Hh_h, e->Spad, e->lw[0].w2, e->Spad, M, D, S, TC_EPI_GATED_RESIDUAL,
                              e->W(blk(0, c.use_swiglu ? "mlp.w3.bias" : "mlp.fc2.bias")).d);
       a.out = e->X; a.ldo = D; a.mod = e->mod; a.mod_ld = e->NMx; a.gate_off = mo.gate_mlp; a.T = T;
-      if (fused) { a.nx_w = e->W(blk(0, "norm1.weight")).d; a.nx_scale_off = mo.scale_msa; a.nx_A = e->A_h; a.nx_part = e->part2; }
+      if (fused) {
+        a.nx_w = e->W(blk(0, "norm1.weight")).d; a.nx_scale_off = mo.scale_msa; a.nx_A = e->A_h; a.nx_part = e->part2;
+        a.nx_part_ld = gemm_tc_part_ld(D, gemm_tc_part_coarse(a));
+      }
       launch_gemm_tc(a, s);
     };
   } else if (k == "attention") {

@@ -5,7 +5,7 @@
 
 namespace vv {
 
-constexpr int GB_M = 64, GB_N = 64, GB_K = 16;
+constexpr int GB_M = 64, GB_N = 64;
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -14,10 +14,14 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
 }
 
-template <bool VEC>
+// GB_K: K extent of one shared-memory tile.  Every output element accumulates its products in ascending k with one
+// fmaf chain whatever GB_K is, so the tile depth changes the schedule, never the result: 16 for large problems, 64 for
+// the single-row-tile conditioning GEMMs (M <= 64), whose duration is K / GB_K exposed global-load latencies.
+template <bool VEC, int GB_K>
 __global__ void __launch_bounds__(256) k_gemm_f32(F32GemmArgs a) {
   __shared__ __align__(16) float As[GB_K][GB_M + 4];
   __shared__ __align__(16) float Ws[GB_K][GB_N + 4];
+  constexpr int NV = GB_K / 16;    // float4 loads per thread, per operand, per tile
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
   const int tx = tid & 15, ty = tid >> 4;  // 16x16 threads, 4x4 outputs each
@@ -28,32 +32,40 @@ __global__ void __launch_bounds__(256) k_gemm_f32(F32GemmArgs a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int lr = tid >> 2;         // 0..63 : tile row loaded by this thread
-  const int lk = (tid & 3) * 4;    // 0,4,8,12 : k offset
+  const int lk = (tid & 3) * 4;    // 0,4,8,12 : k offset inside a 16-wide slice of the tile
   for (int k0 = 0; k0 < a.K; k0 += GB_K) {
-    float av[4] = {0.f, 0.f, 0.f, 0.f}, wv[4] = {0.f, 0.f, 0.f, 0.f};
-    int gm = m0 + lr, gn = n0 + lr, gk = k0 + lk;
-    if (VEC) {
-      if (gm < a.M && gk < a.K) {
-        float4 t = *reinterpret_cast<const float4*>(a.A + (size_t)gm * a.lda + gk);
-        av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
-      }
-      if (gn < a.N && gk < a.K) {
-        float4 t = *reinterpret_cast<const float4*>(a.W + (size_t)gn * a.ldw + gk);
-        wv[0] = t.x; wv[1] = t.y; wv[2] = t.z; wv[3] = t.w;
-      }
-    } else {
+    float av[NV][4], wv[NV][4];
+    const int gm = m0 + lr, gn = n0 + lr;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (gm < a.M && gk + i < a.K) av[i] = a.A[(size_t)gm * a.lda + gk + i];
-        if (gn < a.N && gk + i < a.K) wv[i] = a.W[(size_t)gn * a.ldw + gk + i];
+    for (int v = 0; v < NV; ++v) {
+      const int gk = k0 + v * 16 + lk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[v][i] = wv[v][i] = 0.f;
+      if (VEC) {
+        if (gm < a.M && gk < a.K) {
+          float4 t = *reinterpret_cast<const float4*>(a.A + (size_t)gm * a.lda + gk);
+          av[v][0] = t.x; av[v][1] = t.y; av[v][2] = t.z; av[v][3] = t.w;
+        }
+        if (gn < a.N && gk < a.K) {
+          float4 t = *reinterpret_cast<const float4*>(a.W + (size_t)gn * a.ldw + gk);
+          wv[v][0] = t.x; wv[v][1] = t.y; wv[v][2] = t.z; wv[v][3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (gm < a.M && gk + i < a.K) av[v][i] = a.A[(size_t)gm * a.lda + gk + i];
+          if (gn < a.N && gk + i < a.K) wv[v][i] = a.W[(size_t)gn * a.ldw + gk + i];
+        }
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      As[lk + i][lr] = av[i];
-      Ws[lk + i][lr] = wv[i];
-    }
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        As[v * 16 + lk + i][lr] = av[v][i];
+        Ws[v * 16 + lk + i][lr] = wv[v][i];
+      }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < GB_K; ++kk) {
@@ -102,10 +114,11 @@ void launch_gemm_f32(const F32GemmArgs& a, cudaStream_t s) {
   dim3 grid(cdiv(a.N, GB_N), cdiv(a.M, GB_M));
   bool vec = (a.K % 4 == 0) && (a.lda % 4 == 0) && (a.ldw % 4 == 0) &&
              ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(a.W) & 15) == 0);
-  if (vec)
-    k_gemm_f32<true><<<grid, 256, 0, s>>>(a);
-  else
-    k_gemm_f32<false><<<grid, 256, 0, s>>>(a);
+  const bool deep = grid.y == 1;   // one row tile: latency-bound on the k loop
+  if (vec && deep) k_gemm_f32<true, 64><<<grid, 256, 0, s>>>(a);
+  else if (vec) k_gemm_f32<true, 16><<<grid, 256, 0, s>>>(a);
+  else if (deep) k_gemm_f32<false, 64><<<grid, 256, 0, s>>>(a);
+  else k_gemm_f32<false, 16><<<grid, 256, 0, s>>>(a);
   VV_LAUNCH_CHECK();
 }
 

@@ -186,6 +186,55 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 __device__ __forceinline__ float sumsq4(const float4 x) {
   return fmaf(x.w, x.w, fmaf(x.z, x.z, fmaf(x.y, x.y, x.x * x.x)));
 }
+// ---- RMSNorm partial sums (see TcGemmArgs::nx_part).  s(c, j) = sumsq4 of columns 32c + 4j .. 32c + 4j + 3 of a row.
+//   coarse slot g (one float):   fold8_j( ((s(4g, j) + s(4g+1, j)) + s(4g+2, j)) + s(4g+3, j) )
+//   fine slots of chunk c (eight floats):  s(c, 0..7)
+// fold8 is the order of an 8-lane xor-butterfly (4, 2, 1) as seen by lane 0.
+__device__ __forceinline__ float fold8(const float* s) {
+  return ((s[0] + s[4]) + (s[2] + s[6])) + ((s[1] + s[5]) + (s[3] + s[7]));
+}
+// consumer: total of a row's slots in ascending group order (nslots = coarse slots, or fine chunks)
+__device__ __forceinline__ float part_total(const float* __restrict__ slots, int nslots, int fine) {
+  float total = 0.f;
+  if (!fine) {
+    const float4* pp = reinterpret_cast<const float4*>(slots);
+    const int n4 = (nslots + 3) >> 2;
+#pragma unroll 4
+    for (int i = 0; i < n4; ++i) {
+      const float4 v = pp[i];
+      const int r = nslots - 4 * i;   // valid slots in this quad (stale values may follow the last one)
+      total += v.x;
+      if (r > 1) total += v.y;
+      if (r > 2) total += v.z;
+      if (r > 3) total += v.w;
+    }
+  } else {
+    for (int c0 = 0; c0 < nslots; c0 += 4) {
+      float t[8];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (c0 + cc < nslots) {
+          const float4 lo = *reinterpret_cast<const float4*>(slots + (c0 + cc) * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(slots + (c0 + cc) * 8 + 4);
+          const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = cc == 0 ? v[j] : t[j] + v[j];
+        }
+      }
+      total += fold8(t);
+    }
+  }
+  return total;
+}
+// gated-residual chunk ownership: of the two epilogue warps of a TMEM lane quarter, warp `half` owns the 128-column
+// groups half, half + 2, ... of a tile and walks each group's 32-column chunks in ascending order (so that a coarse
+// slot is accumulated by one lane in a fixed order).  n_chunks = "none left".
+__device__ __forceinline__ int gr_first(int half, int n_chunks) { return half * 4 < n_chunks ? half * 4 : n_chunks; }
+__device__ __forceinline__ int gr_next(int c, int n_chunks) {
+  ++c;
+  if ((c & 3) == 0) c += 4;
+  return c < n_chunks ? c : n_chunks;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -264,15 +313,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
   float in_rstd = 1.f;
   const float* bvec = a.bias;
   if (fusedc) {
-    float ssum = 0.f;
-    // this row's partial sums are contiguous (32 slots = one 128-byte line): independent 16-byte loads, fixed order
-    const float4* pp = reinterpret_cast<const float4*>(a.in_part + (size_t)(wrow0 + lane) * 32);
-    const int np4 = (a.in_nparts + 3) >> 2;
-    float4 pv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pv[i] = i < np4 ? pp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ssum += ((pv[i].x + pv[i].y) + pv[i].z) + pv[i].w;
+    const float ssum = part_total(a.in_part + (size_t)(wrow0 + lane) * a.in_part_ld, a.in_nslots, a.in_fine);
     in_rstd = rsqrtf(ssum / (float)a.in_dim + 1e-6f);
     bvec = a.sp + (size_t)wb * a.sp_ld;
   }
@@ -312,7 +353,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
       }
     }
   };
-  prefetch(half);
+  prefetch(EPI == TC_EPI_GATED_RESIDUAL ? gr_first(half, n_chunks) : half);
   // consumer epilogues: the per-sample shift.W^T+bias vector lives in the big `mod` matrix (DRAM latency): request
   // the vectors of all (<= 4) chunks this warp will process before waiting for the accumulator
   constexpr bool kBiasAhead = EPI == TC_EPI_SWIGLU || EPI == TC_EPI_EMBED || EPI == TC_EPI_BIAS_F32;  // (QKV: register budget, stays one-ahead)
@@ -325,10 +366,9 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  float ssacc[LPR];
+  float ssacc[LPR];   // gated residual, coarse slots: this lane's sums of squares over the current 128-column group
 #pragma unroll
   for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
-
   // QKV: head index / in-head offset by multiply-high (exact for col * hd < 2^32) instead of integer division
   const int qD = EPI == TC_EPI_QKV ? a.H * a.hd : 1;
   const uint32_t hd_magic = EPI == TC_EPI_QKV ? 0xFFFFFFFFu / (uint32_t)a.hd + 1u : 0u;
@@ -396,7 +436,7 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
     const float4 bb = kBiasAhead ? bb_ahead : bb_n, g1 = g_n;
     const float4 cw = make_float4(nw_n.x * (1.f + ns_n.x), nw_n.y * (1.f + ns_n.y), nw_n.z * (1.f + ns_n.z),
                                   nw_n.w * (1.f + ns_n.w));
-    if (!kBiasAhead) prefetch(c + 2);
+    if (!kBiasAhead) prefetch(EPI == TC_EPI_GATED_RESIDUAL ? gr_next(c, n_chunks) : c + 2);
     ptx::tmem_ld_wait();
 
     // stage the 32 x 32 fp32 block (thread == row), scaled by 1/rms when the norm is fused
@@ -417,10 +457,23 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
         x.z = fmaf(g1.z, v.z + bb.z, x.z); x.w = fmaf(g1.w, v.w + bb.w, x.w);
         if (!(a.experiment & 4)) *reinterpret_cast<float4*>(xo + ps * xpass) = x;
         if (a.nx_w) {
-          ssacc[ps] += sumsq4(x);
+          const float sq = sumsq4(x);   // s(chunk, lane & 7) of row ps * 4 + prow
+          if (a.nx_coarse) ssacc[ps] = (c & 3) == 0 ? sq : ssacc[ps] + sq;
+          else a.nx_part[(size_t)(wrow0 + ps * RPP + prow) * a.nx_part_ld + ((n0 + c0) >> 5) * 8 + (lane & 7)] = sq;
           if (!(a.experiment & 2))
           *reinterpret_cast<uint2*>(nxptr + c0 + ps * xpass) =
               make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
+        }
+      }
+      if (a.nx_w && a.nx_coarse && (((c + 1) & 3) == 0 || c + 1 >= n_chunks)) {
+        // the 128-column group is complete: butterfly over the row's eight lanes, one coarse slot per row
+#pragma unroll
+        for (int ps = 0; ps < LPR; ++ps) {
+          float v = ssacc[ps];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          if ((lane & 7) == 0) a.nx_part[(size_t)(wrow0 + ps * RPP + prow) * a.nx_part_ld + ((n0 + c0) >> 7)] = v;
         }
       }
     } else if (EPI == TC_EPI_EMBED) {
@@ -601,16 +654,10 @@ __device__ __forceinline__ void epi_tile_fast(const TcGemmArgs& a, const uint32_
       if (c < n_chunks) chunk_body(c, bball[ci]);
     }
   } else {
-    for (int c = half; c < n_chunks; c += 2) chunk_body(c, make_float4(0.f, 0.f, 0.f, 0.f));
-  }
-  if (EPI == TC_EPI_GATED_RESIDUAL && a.nx_w) {
-#pragma unroll
-    for (int ps = 0; ps < LPR; ++ps) {
-      float v = ssacc[ps];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      if ((lane & 7) == 0) a.nx_part[(size_t)(wrow0 + ps * RPP + prow) * 32 + (n_blk * 2 + half)] = v;
+    if (EPI == TC_EPI_GATED_RESIDUAL) {
+      for (int c = gr_first(half, n_chunks); c < n_chunks; c = gr_next(c, n_chunks)) chunk_body(c, make_float4(0.f, 0.f, 0.f, 0.f));
+    } else {
+      for (int c = half; c < n_chunks; c += 2) chunk_body(c, make_float4(0.f, 0.f, 0.f, 0.f));
     }
   }
 }
@@ -918,7 +965,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     };
     if (EPI == TC_EPI_GATED_RESIDUAL_TMA) {
       // every tile is interior and the warp's 32 rows belong to one sample (launch_gemm_tc checked it)
-      const int NH = a.xt_warps >> 2;   // warps per TMEM lane quarter (1 or 2); warp `half` takes chunks half, half + NH, ...
+      // Column chunks are owned in 128-column GROUPS (four 32-column chunks): with NH warps per TMEM lane quarter
+      // (xt_warps / 4 = 1 or 2) warp `half` takes groups half, half + NH, ... of a tile and walks each group's chunks
+      // in ascending order - so a coarse partial-sum slot, ((f0+f1)+f2)+f3, is built by one thread in a fixed order.
+      const int NH = a.xt_warps >> 2;
       if (half < NH) {
       const int NS = a.xt_slots, ew = half * 4 + q, NW = a.xt_warps;
       const uint32_t epi_s = ptx::smem_u32(staging);
@@ -927,17 +977,32 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t vs = epi_s + (uint32_t)(NW * NS) * XT_BYTES + (uint32_t)NW * NXT_BYTES + (uint32_t)(ew * (32 / NW)) * VEC_BYTES;
       uint64_t* xbar = bars->xfull[ew];
       const bool has_nx = a.nx_w != nullptr;
+      const bool coarse = a.nx_coarse != 0;
+      auto tile_chunks = [&](int tile) { return ((tile % n_tiles == n_tiles - 1) ? BNlast : BN) >> 5; };
+      // next chunk of this warp after chunk c of a tile with nch chunks; -1: the tile is finished
+      auto next_chunk = [&](int c, int nch) {
+        ++c;
+        if ((c & 3) == 0 || c >= nch) {               // group finished
+          c = (((c - 1) >> 2) + NH) << 2;
+          if (c >= nch) c = -1;
+        }
+        return c;
+      };
+      auto first_chunk = [&](int nch) { return half * 4 < nch ? half * 4 : -1; };
       // this warp's (tile, chunk) stream; `ld_*` runs NS positions ahead of the chunk being processed
-      int ld_tile = sched_id, ld_c = half;
+      int ld_tile = sched_id, ld_c = -1;
+      auto ld_seek = [&]() {   // first tile from ld_tile on in which this warp owns a chunk
+        while (ld_tile < num_tiles && (ld_c = first_chunk(tile_chunks(ld_tile))) < 0) ld_tile += sched_n;
+      };
+      ld_seek();
       auto ld_issue = [&](int slot) {   // lane 0 only
         if (ld_tile >= num_tiles) return;
         const int mb = a.reverse_m ? m_tiles - 1 - ld_tile / n_tiles : ld_tile / n_tiles, nb = ld_tile % n_tiles;
         const int row0 = mb * tile_m + (int)rank * TC_BM + q * 32, col0 = nb * BN + ld_c * 32;
         ptx::mbar_expect_tx(&xbar[slot], XT_BYTES);
         tma_load_tile(xs + (uint32_t)slot * XT_BYTES, &tmX, ptx::smem_u32(&xbar[slot]), col0, row0);
-        const int nch = ((nb == n_tiles - 1) ? BNlast : BN) >> 5;
-        ld_c += NH;
-        if (ld_c >= nch) { ld_tile += sched_n; ld_c = half; }
+        ld_c = next_chunk(ld_c, tile_chunks(ld_tile));
+        if (ld_c < 0) { ld_tile += sched_n; ld_seek(); }
       };
       if (lane == 0)
         for (int i = 0; i < NS; ++i) ld_issue(i);
@@ -945,16 +1010,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
         const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
-        const int n_chunks = ((n_blk == n_tiles - 1) ? BNlast : BN) >> 5;
+        const int n_chunks = tile_chunks(tile);
         const int wrow0 = m0 + q * 32;
         const int wb = wrow0 / a.T;
         const float* modrow = a.mod + (size_t)wb * a.mod_ld;
-        // per-column vectors of the tile (lane = column): bias, gate, and the next norm's w * (1 + scale)
+        // per-column vectors of this warp's chunks (lane = column): bias, gate, and the next norm's w * (1 + scale)
         __syncwarp();
-#pragma unroll
-        for (int ci = 0; ci < 8; ++ci) {
-          const int c = half + ci * NH;
-          if (c < n_chunks) {
+        {
+          int ci = 0;
+          for (int c = first_chunk(n_chunks); c >= 0; c = next_chunk(c, n_chunks), ++ci) {
             const int col = n0 + c * 32 + lane;
             const float bv = a.bias ? a.bias[col] : 0.f;
             const float gv = modrow[a.gate_off + col];
@@ -969,20 +1033,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::mbar_wait(&bars->tfull[as], aphase);
         ptx::tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
-        float ss[2][8];   // partial sums of the even / odd chunks (the slot grouping of the eight-warp epilogues)
+        int c = first_chunk(n_chunks);
+        if (c < 0) release_acc(as);      // a narrow tile none of whose groups is this warp's
+        float gs[8];                     // this row's sums of squares over the current 128-column group (coarse slots)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss[0][i] = ss[1][i] = 0.f;
-#pragma unroll 2
-        for (int ci = 0; ci < 8; ++ci) {
-          const int c = half + ci * NH;
-          if (c >= n_chunks) break;
+        for (int j = 0; j < 8; ++j) gs[j] = 0.f;
+        for (int ci = 0; c >= 0; ++ci) {
+          const int cn = next_chunk(c, n_chunks);
           const uint32_t xt = xs + slot * XT_BYTES + (uint32_t)lane * 128;
           uint32_t r[32];
           ptx::tmem_ld_x32(tbase + (uint32_t)(c * 32), r);
           ptx::mbar_wait(&xbar[slot], sphase);          // the residual tile of this chunk has landed
           ptx::tmem_ld_wait();
-          if (c + NH >= n_chunks) release_acc(as);      // last read of this accumulator stage by this warp
+          if (cn < 0) release_acc(as);                  // last read of this accumulator stage by this warp
           uint32_t nxw[16];
+          float ss[8];
           const uint32_t vb = vs + (uint32_t)ci * VEC_BYTES;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -996,7 +1061,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             sts128(xa, x.x, x.y, x.z, x.w);
             if (has_nx) {
               const float4 c4 = lds128(vb + 256 + j4 * 16);
-              if (c & 1) ss[1][j4] += sumsq4(x); else ss[0][j4] += sumsq4(x);
+              ss[j4] = sumsq4(x);
               nxw[j4 * 2] = pack_bf16(x.x * c4.x, x.y * c4.y);
               nxw[j4 * 2 + 1] = pack_bf16(x.z * c4.z, x.w * c4.w);
             }
@@ -1008,6 +1073,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(na + jj * 16), "r"(nxw[jj * 4]),
                            "r"(nxw[jj * 4 + 1]), "r"(nxw[jj * 4 + 2]), "r"(nxw[jj * 4 + 3])
                            : "memory");
+            // partial sums of x'^2: eight fine slots per chunk, or one coarse slot per 128-column group
+            float* prow_ = a.nx_part + (size_t)(wrow0 + lane) * a.nx_part_ld;
+            const int gc = (n0 >> 5) + c;               // global chunk index
+            if (!coarse) {
+              *reinterpret_cast<float4*>(prow_ + gc * 8) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+              *reinterpret_cast<float4*>(prow_ + gc * 8 + 4) = make_float4(ss[4], ss[5], ss[6], ss[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gs[j] = (c & 3) == 0 ? ss[j] : gs[j] + ss[j];
+              if ((c & 3) == 3 || c + 1 >= n_chunks) prow_[gc >> 2] = fold8(gs);
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -1021,15 +1097,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           __syncwarp();                    // no lane rewrites the operand tile before the store has read it
           if (++slot == (uint32_t)NS) { slot = 0; sphase ^= 1u; }
-        }
-        if (has_nx) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h < n_chunks && (NH == 1 || h == half)) {
-              const float v = ((ss[h][0] + ss[h][4]) + (ss[h][2] + ss[h][6])) + ((ss[h][1] + ss[h][5]) + (ss[h][3] + ss[h][7]));
-              a.nx_part[(size_t)(wrow0 + lane) * 32 + (n_blk * 2 + h)] = v;
-            }
-          }
+          c = cn;
         }
         as ^= 1;
         if (as == 0) aphase ^= 1;
@@ -1070,20 +1138,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
       };
-      prefetch_x(half);
+      const bool grouped = EPI == TC_EPI_GATED_RESIDUAL && CW == 32;   // chunk ownership by 128-column groups
+      prefetch_x(grouped ? gr_first(half, n_chunks) : half);
       // fused-norm consumer: this row's 1/rms from the producer's partial sums (fixed summation order)
       float in_rstd = 1.f;
       if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part) {
         float ssum = 0.f;
-        if (my_row < a.M)
-        {
-          const float4* pp = reinterpret_cast<const float4*>(a.in_part + (size_t)my_row * 32);
-          const int np4 = (a.in_nparts + 3) >> 2;
-          for (int i = 0; i < np4; ++i) {
-            const float4 pv = pp[i];
-            ssum += ((pv.x + pv.y) + pv.z) + pv.w;
-          }
-        }
+        if (my_row < a.M) ssum = part_total(a.in_part + (size_t)my_row * a.in_part_ld, a.in_nslots, a.in_fine);
         in_rstd = rsqrtf(ssum / (float)a.in_dim + 1e-6f);
       }
       // per-row bias source: per-sample vector sp[b,:] when the norm is fused, else the plain bias
@@ -1093,9 +1154,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const float* bwarp = a.bias;  // same, for the warp's (single) sample in the row-wise pass
       if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part)
         bwarp = a.sp + (size_t)min(wb, (a.M - 1) / a.T) * a.sp_ld;
-      float ssacc[LPR];
-#pragma unroll
-      for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
 
       // Per-column vectors of a chunk in the row-wise pass: bias (or the fused per-sample sp vector), and for the
       // gated residual the gate and the next norm's w*(1+scale).  sp / gate / scale live in the big `mod` matrix
@@ -1115,7 +1173,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       };
       float4 bb_n, g1_n, cw_n;
-      load_vecs(half, bb_n, g1_n, cw_n);
+      load_vecs(grouped ? gr_first(half, n_chunks) : half, bb_n, g1_n, cw_n);
+      float ssacc[LPR];
+#pragma unroll
+      for (int ps = 0; ps < LPR; ++ps) ssacc[ps] = 0.f;
 
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after();
@@ -1125,8 +1186,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       float qk_mean = 0.f, qk_rstd = 1.f;
       int qk_head = -1;
 
-      for (int c = half; c < n_chunks; c += 2) {
+      for (int c = grouped ? gr_first(half, n_chunks) : half; c < n_chunks; c = grouped ? gr_next(c, n_chunks) : c + 2) {
         const int c0 = c * CW;
+        const int c_next = grouped ? gr_next(c, n_chunks) : c + 2;
         uint32_t r[CW];
         if (CW == 32) ptx::tmem_ld_x32(tbase + c0, r);
         else ptx::tmem_ld_x16(tbase + c0, r);
@@ -1134,11 +1196,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (EPI == TC_EPI_GATED_RESIDUAL) {
 #pragma unroll
           for (int ps = 0; ps < LPR; ++ps) xcur[ps] = xpre[ps];
-          prefetch_x(c + 2);
+          prefetch_x(c_next);
         }
         // per-column vectors of this chunk were requested one chunk ago; request the next chunk's now
         const float4 bb = bb_n, g1 = g1_n, cw = cw_n;
-        load_vecs(c + 2, bb_n, g1_n, cw_n);
+        load_vecs(c_next, bb_n, g1_n, cw_n);
         ptx::tmem_ld_wait();
         if ((EPI == TC_EPI_QKV || EPI == TC_EPI_SWIGLU || EPI == TC_EPI_GELU_BF16) && a.in_part) {
 #pragma unroll
@@ -1259,19 +1321,37 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int ps = 0; ps < LPR; ++ps) {
             const int rr = ps * RPP + prow;
             const int row = wrow0 + rr;
-            if (row >= a.M || !col_ok) continue;
-            float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + pcc);
-            float4 g = g1;
-            if (!rows_one_sample)
-              g = *reinterpret_cast<const float4*>(a.mod + (size_t)(row / a.T) * a.mod_ld + a.gate_off + col);
-            float4 x = xcur[ps];
-            x.x = fmaf(g.x, v.x + bb.x, x.x); x.y = fmaf(g.y, v.y + bb.y, x.y);
-            x.z = fmaf(g.z, v.z + bb.z, x.z); x.w = fmaf(g.w, v.w + bb.w, x.w);
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = x;
-            if (a.nx_w) {
-              ssacc[ps] += sumsq4(x);
-              *reinterpret_cast<uint2*>(a.nx_A + (size_t)row * a.ldo + col) =
-                  make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
+            const bool ok = row < a.M && col_ok;
+            float sq = 0.f;
+            if (ok) {
+              float4 v = *reinterpret_cast<const float4*>(st + rr * (CW + 4) + pcc);
+              float4 g = g1;
+              if (!rows_one_sample)
+                g = *reinterpret_cast<const float4*>(a.mod + (size_t)(row / a.T) * a.mod_ld + a.gate_off + col);
+              float4 x = xcur[ps];
+              x.x = fmaf(g.x, v.x + bb.x, x.x); x.y = fmaf(g.y, v.y + bb.y, x.y);
+              x.z = fmaf(g.z, v.z + bb.z, x.z); x.w = fmaf(g.w, v.w + bb.w, x.w);
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + (size_t)row * a.ldo + col) = x;
+              if (a.nx_w) {
+                sq = sumsq4(x);
+                *reinterpret_cast<uint2*>(a.nx_A + (size_t)row * a.ldo + col) =
+                    make_uint2(pack_bf16(x.x * cw.x, x.y * cw.y), pack_bf16(x.z * cw.z, x.w * cw.w));
+              }
+            }
+            if (a.nx_w && CW == 32) {   // (launch_gemm_tc: N % 32 == 0, so a chunk's columns are all valid or all invalid)
+              if (a.nx_coarse) ssacc[ps] = (c & 3) == 0 ? sq : ssacc[ps] + sq;
+              else if (ok) a.nx_part[(size_t)row * a.nx_part_ld + ((n0 + c0) >> 5) * 8 + (lane & 7)] = sq;
+            }
+          }
+          if (a.nx_w && CW == 32 && a.nx_coarse && (((c + 1) & 3) == 0 || c + 1 >= n_chunks)) {   // 128-column group complete
+#pragma unroll
+            for (int ps = 0; ps < LPR; ++ps) {
+              float v = ssacc[ps];
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              const int row = wrow0 + ps * RPP + prow;
+              if ((lane & 7) == 0 && row < a.M) a.nx_part[(size_t)row * a.nx_part_ld + ((n0 + c0) >> 7)] = v;
             }
           }
           continue;
@@ -1344,17 +1424,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint32_t pk = pack_bf16(silu_fast(v.x) * v.y, silu_fast(v.z) * v.w);
             *reinterpret_cast<uint32_t*>(reinterpret_cast<bf16*>(a.out) + (size_t)row * a.ldo + (col >> 1)) = pk;
           }
-        }
-      }
-      if (EPI == TC_EPI_GATED_RESIDUAL && a.nx_w) {
-        // per-row partial sum of squares over this warp's column chunks of this tile -> fixed slot (no atomics)
-#pragma unroll
-        for (int ps = 0; ps < LPR; ++ps) {
-          float v = ssacc[ps];
-#pragma unroll
-          for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          const int row = wrow0 + ps * RPP + prow;
-          if ((lane % LPR) == 0 && row < a.M) a.nx_part[(size_t)row * 32 + (n_blk * 2 + half)] = v;
         }
       }
       // release this accumulator stage to the MMA warp
@@ -1450,7 +1519,9 @@ static bool layer_gemm(const TcGemmArgs& a) {
   // attn.proj (K <= N, bandwidth-bound on its residual traffic) measured 3-4 % faster on 192-wide tiles: more, smaller
   // tiles keep more residual loads in flight; the main-loop-bound GEMMs want the wide tiles
   const bool gated = a.epi == TC_EPI_GATED_RESIDUAL || a.epi == TC_EPI_GATED_RESIDUAL_TMA;
-  if (gated && a.K <= a.N && bn_mode() == 0) return false;
+  // (attn.proj used to prefer 192-wide tiles with the register-prefetch epilogue; with the TMA epilogue the 256-wide
+  //  tiling measured +8 % isolated and neutral in the sampler, and whole 128-column groups per tile are what coarse
+  //  partial-sum slots need)
   return gated || a.epi == TC_EPI_SWIGLU || a.epi == TC_EPI_GELU_BF16 ||
          (a.epi == TC_EPI_QKV && !a.qn_w && (a.H * a.hd) % 32 == 0);
 }
@@ -1605,6 +1676,39 @@ static void launch_epi(const TcGemmArgs& a, int BN, int cw, cudaStream_t s) {
   else launch_inst<EPI, 16>(a, BN, s);
 }
 
+// How a gated-residual launch runs: register-prefetch epilogue or TMA epilogue (warps, ring depth), and which kind
+// of partial-sum slots it writes.  One function, so that the engine can ask what its consumer will find.
+struct GatedPlan { bool tma; int warps, slots, coarse; };
+static GatedPlan gated_plan(const TcGemmArgs& a, int BN) {
+  GatedPlan p = {false, 8, 2, 0};
+  // VAVAE_GEMM_TMA_EPI (developer knob, same-box A/B): 0 = never, 1 = every eligible launch,
+  // 2 (default) = where it measured faster: attn.proj (K <= N: epilogue-bound), the long-K mlp.w3 of the XL model
+  // (main-loop-bound: four epilogue warps keep all five operand stages), and every small-M launch on narrow tiles
+  static int tma_epi = -1;
+  if (tma_epi < 0) { const char* e = std::getenv("VAVAE_GEMM_TMA_EPI"); tma_epi = e ? std::atoi(e) : 2; }
+  static int exp_mode = -1;
+  if (exp_mode < 0) { const char* e = std::getenv("VAVAE_GEMM_EXPERIMENT"); exp_mode = e ? std::atoi(e) : 0; }
+  const int BNl = gemm_tc_last_bn(a, BN);
+  // guard-free geometry: whole 256-row tile pairs, whole 32-column chunks, 32-row groups inside one sample, 16-byte pitches
+  const bool eligible = BN % 32 == 0 && BN <= 256 && BNl % 32 == 0 && a.T > 0 && a.T % 32 == 0 && a.M % (2 * TC_BM) == 0 &&
+                        (a.N % BN == 0 || a.N % BN == BNl) && a.ldo % 8 == 0 && a.N <= a.ldo &&
+                        (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                        (!a.nx_w || (reinterpret_cast<uintptr_t>(a.nx_A) & 15) == 0) && a.mod != nullptr;
+  const bool wanted = tma_epi == 1 || a.K <= a.N || a.K >= 3072 || BN <= 128;
+  p.tma = tma_epi != 0 && exp_mode == 0 && eligible && wanted;
+  if (p.tma) {
+    static int xt_env = -1;   // VAVAE_GEMM_XT_SLOTS: developer knob, ring depth per epilogue warp
+    if (xt_env < 0) { const char* e = std::getenv("VAVAE_GEMM_XT_SLOTS"); xt_env = e ? std::atoi(e) : 0; }
+    p.slots = (xt_env >= 2 && xt_env <= XT_MAX_SLOTS) ? xt_env : 2;
+    p.warps = (a.K <= a.N && BN > 128) ? 8 : 4;
+  }
+  // a CTA (and within it one warp) must own whole 128-column groups
+  p.coarse = (BN % 128 == 0 && BNl % 128 == 0) ? 1 : 0;
+  return p;
+}
+int gemm_tc_part_coarse(const TcGemmArgs& a) { return gated_plan(a, gemm_tc_pick_bn(a)).coarse; }
+int gemm_tc_part_ld(int n_cols, int coarse) { return coarse ? 16 : n_cols / 4; }
+
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
   VV_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tc: empty problem");
   VV_CHECK(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm_tc: row pitch must be a multiple of 8 bf16 (16 bytes)");
@@ -1635,25 +1739,15 @@ void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {
       if (exp_mode < 0) { const char* e = std::getenv("VAVAE_GEMM_EXPERIMENT"); exp_mode = e ? std::atoi(e) : 0; }
       TcGemmArgs b = a;
       b.experiment = exp_mode;
-      // the TMA epilogue needs guard-free geometry: whole 256-row tile pairs, whole 32-column chunks, 32-row groups
-      // inside one sample, 16-byte row pitches.  VAVAE_GEMM_TMA_EPI=0: developer knob (same-box A/B)
-      static int tma_epi = -1;
-      if (tma_epi < 0) { const char* e = std::getenv("VAVAE_GEMM_TMA_EPI"); tma_epi = e ? std::atoi(e) : 2; }
-      const int BNl = gemm_tc_last_bn(a, BN);
-      // 1: every eligible launch;
-      // 2 (default): where it measured faster - attn.proj (K <= N: epilogue-bound, eight epilogue warps) and the long-K
-      // mlp.w3 of the XL model (main-loop-bound: four epilogue warps, all five operand stages kept)
-      const bool tma_ok = tma_epi && (tma_epi == 1 || a.K <= a.N || a.K >= 3072) && exp_mode == 0 && BN <= 256 && cw == 32 && a.T > 0 && a.T % 32 == 0 && a.M % (2 * TC_BM) == 0 &&
-                          BN % 32 == 0 && BNl % 32 == 0 && (a.N % BN == 0 || a.N % BN == BNl) && a.ldo % 8 == 0 &&
-                          a.N <= a.ldo && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
-                          (!a.nx_w || (reinterpret_cast<uintptr_t>(a.nx_A) & 15) == 0) && a.mod != nullptr;
-      if (tma_ok) {
+      VV_CHECK(!a.nx_w || (a.N % 32 == 0 && cw == 32), "gemm_tc: the fused next-norm producer needs N % 32 == 0");
+      const GatedPlan plan = gated_plan(a, BN);
+      b.nx_coarse = plan.coarse;
+      VV_CHECK(!a.nx_w || a.nx_part_ld >= gemm_tc_part_ld(a.N, plan.coarse), "gemm_tc: partial-sum row pitch too small");
+      VV_CHECK(!a.nx_w || !plan.coarse || a.N <= 2048, "gemm_tc: coarse partial sums cover at most 2048 columns");
+      if (plan.tma) {
         b.epi = TC_EPI_GATED_RESIDUAL_TMA;
-        // ring depth per epilogue warp (VAVAE_GEMM_XT_SLOTS: developer knob)
-        static int xt_env = -1;
-        if (xt_env < 0) { const char* e = std::getenv("VAVAE_GEMM_XT_SLOTS"); xt_env = e ? std::atoi(e) : 0; }
-        b.xt_slots = (xt_env >= 2 && xt_env <= XT_MAX_SLOTS) ? xt_env : 2;
-        b.xt_warps = a.K <= a.N ? 8 : 4;
+        b.xt_slots = plan.slots;
+        b.xt_warps = plan.warps;
         launch_epi<TC_EPI_GATED_RESIDUAL_TMA>(b, BN, cw, s);
       } else {
         launch_epi<TC_EPI_GATED_RESIDUAL>(b, BN, cw, s);

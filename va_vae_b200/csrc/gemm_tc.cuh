@@ -51,18 +51,27 @@ struct TcGemmArgs {
   // final
   int p, Cout, Ckeep, img;
   RowMap rm;
-  // ---- RMSNorm + modulate fused across GEMMs (requires T % 32 == 0) --------------------------------------
+  // ---- RMSNorm + modulate fused across GEMMs (requires T % 32 == 0, N % 32 == 0 on the producer) ---------------
   // producer side (TC_EPI_GATED_RESIDUAL): besides x_new, write the NEXT GEMM's operand
   //   nx_A[row, col] = bf16(x_new * nx_w[col] * (1 + mod[b, nx_scale_off + col]))        (un-normalised)
-  // and per-row partial sums of x_new^2: nx_part[(n_tile*2 + half) * M + row]
+  // and per-row partial sums of x_new^2 in nx_part[row * nx_part_ld + ...].  With s(c, j) = the sum of squares of
+  // columns 32c + 4j .. 32c + 4j + 3, a COARSE slot (one float per 128-column group g) is
+  //   fold8_j( ((s(4g, j) + s(4g+1, j)) + s(4g+2, j)) + s(4g+3, j) )
+  // and the FINE slots of chunk c are the eight floats s(c, 0..7) (row pitch N / 4).  Which of the two a launch writes
+  // is gemm_tc_part_coarse(args): coarse needs one warp to own whole groups, i.e. 128 / 256-wide tiles; the narrow
+  // tiles of small-M launches write fine slots.  Both are pure functions of the row's values and a consumer folds
+  // fine slots into exactly the coarse values, so the tile shape - which depends on M - never changes a result.
   const float* nx_w;
   int nx_scale_off;
   bf16* nx_A;
   float* nx_part;
-  // consumer side (QKV / SWIGLU / GELU): the accumulator row is scaled by rstd = rsqrt(sum(in_part)/in_dim + 1e-6)
-  // and `sp[b, n]` (= shift[b,:] . W[n,:] + bias[n], fp32, row pitch sp_ld) replaces the bias
+  int nx_part_ld;
+  // consumer side (QKV / SWIGLU / GELU): the accumulator row is scaled by rstd = rsqrt(total / in_dim + 1e-6), total =
+  // the row's group sums added in ascending order (in_nslots coarse slots; or, in_fine = 1, in_nslots chunks of fine
+  // slots folded into their groups first), and `sp[b, n]` (= shift[b,:] . W[n,:] + bias[n], fp32, row pitch sp_ld)
+  // replaces the bias
   const float* in_part;
-  int in_nparts, in_dim;
+  int in_part_ld, in_nslots, in_fine, in_dim;
   const float* sp;
   int sp_ld;
   // ---- implicit-GEMM convolution (VA-VAE decoder): A is an NHWC bf16 activation tensor (N_img, H, W, lda channels,
@@ -88,9 +97,15 @@ struct TcGemmArgs {
   // TC_EPI_GATED_RESIDUAL_TMA only (set by launch_gemm_tc): residual tiles per epilogue warp in the shared-memory ring
   int xt_slots;
   int xt_warps;   // 4 or 8 epilogue warps
+  int nx_coarse;  // 1: coarse partial-sum slots (see nx_part)
 };
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s);
+// 1 if this gated-residual launch writes coarse (128-column) partial-sum slots, 0 if fine (32-column) ones
+int gemm_tc_part_coarse(const TcGemmArgs& a);
+// number of slots (coarse) / chunks (fine) a consumer sums, and the row pitch (floats) either layout needs
+inline int gemm_tc_part_slots(int n_cols, int coarse) { return coarse ? (n_cols + 127) / 128 : (n_cols + 31) / 32; }
+int gemm_tc_part_ld(int n_cols, int coarse);
 int gemm_tc_pick_bn(const TcGemmArgs& a);
 // 1: use the CTA-pair (cta_group::2) kernel where the problem allows it; 0: always the 1-CTA kernel
 void set_gemm_two_cta(int on);

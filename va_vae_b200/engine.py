@@ -53,7 +53,8 @@ class VavaeEpilogueTest(ctypes.Structure):
                 ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("vt", ctypes.c_void_p), ("out_bf16", ctypes.c_void_p),
                 ("ldo", ctypes.c_int32), ("X", ctypes.c_void_p), ("mod", ctypes.c_void_p), ("mod_ld", ctypes.c_int32),
                 ("gate_off", ctypes.c_int32), ("nx_w", ctypes.c_void_p), ("nx_scale_off", ctypes.c_int32),
-                ("nx_A", ctypes.c_void_p), ("nx_part", ctypes.c_void_p), ("nparts_out", ctypes.c_int32)]
+                ("nx_A", ctypes.c_void_p), ("nx_part", ctypes.c_void_p), ("nparts_out", ctypes.c_int32),
+                ("in_fine", ctypes.c_int32), ("fine_out", ctypes.c_int32), ("part_ld", ctypes.c_int32)]
 
 
 class VavaeSdeUpdate(ctypes.Structure):
@@ -406,6 +407,7 @@ def test_gemm_epilogue(**fields) -> int:
             setattr(t, k, int(v))
     with torch.cuda.device(dev):
         _check(lib.vavae_test_gemm_epilogue(ctypes.byref(t), ctypes.c_void_p(_stream(dev))))
+    test_gemm_epilogue.fine_out = int(t.fine_out)   # kind of partial-sum slots a producer launch wrote (1 = 32-column)
     return int(t.nparts_out)
 
 
