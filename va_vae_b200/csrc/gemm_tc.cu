@@ -1516,8 +1516,6 @@ static int bn_mode() {
 }
 static bool layer_gemm(const TcGemmArgs& a) {
   if (a.conv_taps || a.gn_part) return false;
-  // attn.proj (K <= N, bandwidth-bound on its residual traffic) measured 3-4 % faster on 192-wide tiles: more, smaller
-  // tiles keep more residual loads in flight; the main-loop-bound GEMMs want the wide tiles
   const bool gated = a.epi == TC_EPI_GATED_RESIDUAL || a.epi == TC_EPI_GATED_RESIDUAL_TMA;
   // (attn.proj used to prefer 192-wide tiles with the register-prefetch epilogue; with the TMA epilogue the 256-wide
   //  tiling measured +8 % isolated and neutral in the sampler, and whole 128-column groups per tile are what coarse
@@ -1532,7 +1530,41 @@ int gemm_tc_last_bn(const TcGemmArgs& a, int BN) {
   if (bn_mode() == 0 && layer_gemm(a) && BN == 256 && rem != 0 && rem % 32 == 0) return rem;
   return BN;
 }
+// Small-M launches (a batch-1 forward has M = 256 token rows): with 256-wide tiles a layer GEMM would occupy 10 - 48 of
+// the 148 SMs and run at the latency of one long main loop.  Narrow tiles spread the columns over (almost) one full
+// wave of CTAs instead: the widest multiple of 32 that divides N and keeps cdiv(M, 128) * N / bn <= 148.  Safe because
+// no result depends on the tile width (per-element K order is fixed; RMSNorm partial sums: see TcGemmArgs::nx_part).
+// The gated-residual producers stay on multiples of 128 columns (coarse partial-sum slots): with narrower tiles they
+// would write fine slots, and what their consumers then re-read per tile costs what the extra CTAs gain
+// (XL/1 batch 1 / 2 / 4 / 8: 2.56 / 2.63 / 2.80 / 3.27 ms -> 2.20 / 2.20 / 2.52 / 2.97; every GEMM narrow: 2.23 / 2.27 /
+// 2.86 / 2.97; consumers only: 2.50 / 2.53 / 2.80 / 3.27 - gpurun_out/r2_narrow2.log).
+// VAVAE_GEMM_NARROW (developer knob, same-box A/B): 0 = off, 1 = every layer GEMM, 2 = consumers only, 3 = default.
+static int narrow_bn(const TcGemmArgs& a, int regular_bn) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = std::getenv("VAVAE_GEMM_NARROW"); enabled = e ? std::atoi(e) : 3; }
+  if (!enabled || a.N % 32 != 0) return regular_bn;
+  const bool gated = a.epi == TC_EPI_GATED_RESIDUAL || a.epi == TC_EPI_GATED_RESIDUAL_TMA;
+  if (gated && enabled == 2) return regular_bn;
+  const int row_ctas = cdiv(a.M, TC_BM);
+  if (row_ctas * cdiv(a.N, regular_bn) >= 111) return regular_bn;   // three quarters of the SMs are busy anyway
+  int best = regular_bn, best_ctas = row_ctas * cdiv(a.N, regular_bn);
+  for (int bn = 32; bn <= 256; bn += 32) {
+    if (a.N % bn) continue;
+    if (gated && enabled == 3 && bn % 128 != 0) continue;
+    const int ctas = row_ctas * (a.N / bn);
+    if (ctas <= 148 && ctas >= best_ctas) { best = bn; best_ctas = ctas; }   // ties: the wider tile
+  }
+  return best;
+}
+
 int gemm_tc_pick_bn(const TcGemmArgs& a) {
+  if (layer_gemm(a) && bn_mode() == 0) {
+    const int regular = (a.N > 256 && a.N % 256 != 0 && (a.N % 256) % 32 == 0) ? 256 : (a.N % 256 == 0 ? 256 : 0);
+    if (regular) {
+      const int nb = narrow_bn(a, regular);
+      if (nb != regular) return nb;
+    }
+  }
   if (layer_gemm(a)) {
     const int mode = bn_mode();
     if (mode > 0 && mode % 32 == 0 && mode <= 256) return mode;
