@@ -193,36 +193,43 @@ __device__ __forceinline__ float sumsq4(const float4 x) {
 __device__ __forceinline__ float fold8(const float* s) {
   return ((s[0] + s[4]) + (s[2] + s[6])) + ((s[1] + s[5]) + (s[3] + s[7]));
 }
-// consumer: total of a row's slots in ascending group order (nslots = coarse slots, or fine chunks)
-__device__ __forceinline__ float part_total(const float* __restrict__ slots, int nslots, int fine) {
+// consumer: total of a row's slots in ascending group order (nslots = coarse slots, or fine chunks).  The fine form is
+// only met on small or odd-shaped problems and is kept out of line so that it does not weigh on the register allocation
+// of the consumer epilogues (the QKV epilogue sits at the 168-register cap).
+__device__ __noinline__ float part_total_fine(const float* __restrict__ slots, int nslots) {
   float total = 0.f;
-  if (!fine) {
-    const float4* pp = reinterpret_cast<const float4*>(slots);
-    const int n4 = (nslots + 3) >> 2;
-#pragma unroll 4
-    for (int i = 0; i < n4; ++i) {
-      const float4 v = pp[i];
-      const int r = nslots - 4 * i;   // valid slots in this quad (stale values may follow the last one)
-      total += v.x;
-      if (r > 1) total += v.y;
-      if (r > 2) total += v.z;
-      if (r > 3) total += v.w;
-    }
-  } else {
-    for (int c0 = 0; c0 < nslots; c0 += 4) {
-      float t[8];
+  for (int c0 = 0; c0 < nslots; c0 += 4) {
+    float t[8];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        if (c0 + cc < nslots) {
-          const float4 lo = *reinterpret_cast<const float4*>(slots + (c0 + cc) * 8);
-          const float4 hi = *reinterpret_cast<const float4*>(slots + (c0 + cc) * 8 + 4);
-          const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    for (int cc = 0; cc < 4; ++cc) {
+      if (c0 + cc < nslots) {
+        const float4 lo = *reinterpret_cast<const float4*>(slots + (c0 + cc) * 8);
+        const float4 hi = *reinterpret_cast<const float4*>(slots + (c0 + cc) * 8 + 4);
+        const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = cc == 0 ? v[j] : t[j] + v[j];
-        }
+        for (int j = 0; j < 8; ++j) t[j] = cc == 0 ? v[j] : t[j] + v[j];
       }
-      total += fold8(t);
     }
+    total += fold8(t);
+  }
+  return total;
+}
+__device__ __forceinline__ float part_total(const float* __restrict__ slots, int nslots, int fine) {
+  if (fine) return part_total_fine(slots, nslots);
+  // coarse: at most 16 slots (2048 columns); independent 16-byte loads, then the adds in ascending order
+  const float4* pp = reinterpret_cast<const float4*>(slots);
+  const int n4 = (nslots + 3) >> 2;
+  float4 pv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pv[i] = i < n4 ? pp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float total = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = nslots - 4 * i;   // valid slots in this quad (stale values may follow the last one)
+    if (r > 0) total += pv[i].x;
+    if (r > 1) total += pv[i].y;
+    if (r > 2) total += pv[i].z;
+    if (r > 3) total += pv[i].w;
   }
   return total;
 }
@@ -1006,30 +1013,47 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       };
       if (lane == 0)
         for (int i = 0; i < NS; ++i) ld_issue(i);
+      // chunk number ci of this warp in a tile (its valid chunks are a prefix of ci = 0 .. 7)
+      auto chunk_of = [&](int ci) { return 4 * (half + (ci >> 2) * NH) + (ci & 3); };
+      float pv_b[8], pv_g[8], pv_w[8], pv_s[8];   // next tile's bias / gate / norm weight / adaLN scale, lane = column
+      auto vec_load = [&](int tile) {
+        const int mb = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, nb = tile % n_tiles;
+        const int nch = tile_chunks(tile);
+        const float* mr = a.mod + (size_t)((mb * tile_m + (int)rank * TC_BM + q * 32) / a.T) * a.mod_ld;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c = chunk_of(ci);
+          if (c < nch) {
+            const int col = nb * BN + c * 32 + lane;
+            pv_b[ci] = a.bias ? a.bias[col] : 0.f;
+            pv_g[ci] = mr[a.gate_off + col];
+            if (has_nx) { pv_w[ci] = a.nx_w[col]; pv_s[ci] = mr[a.nx_scale_off + col]; }
+          }
+        }
+      };
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) pv_b[ci] = pv_g[ci] = pv_w[ci] = pv_s[ci] = 0.f;
+      if (sched_id < num_tiles) vec_load(sched_id);
       uint32_t slot = 0, sphase = 0;   // ring position of the chunk being processed
       for (int tile = sched_id; tile < num_tiles; tile += sched_n) {
         const int m_blk = a.reverse_m ? m_tiles - 1 - tile / n_tiles : tile / n_tiles, n_blk = tile % n_tiles;
         const int m0 = m_blk * tile_m + (int)rank * TC_BM, n0 = n_blk * BN;
         const int n_chunks = tile_chunks(tile);
         const int wrow0 = m0 + q * 32;
-        const int wb = wrow0 / a.T;
-        const float* modrow = a.mod + (size_t)wb * a.mod_ld;
-        // per-column vectors of this warp's chunks (lane = column): bias, gate, and the next norm's w * (1 + scale)
+        // per-column vectors of this warp's chunks (lane = column): bias, gate, and the next norm's w * (1 + scale).
+        // They were requested one tile ago (vec_load below), so their L2 / DRAM latency is off the tile's critical path.
         __syncwarp();
-        {
-          int ci = 0;
-          for (int c = first_chunk(n_chunks); c >= 0; c = next_chunk(c, n_chunks), ++ci) {
-            const int col = n0 + c * 32 + lane;
-            const float bv = a.bias ? a.bias[col] : 0.f;
-            const float gv = modrow[a.gate_off + col];
-            const float cv = has_nx ? a.nx_w[col] * (1.f + modrow[a.nx_scale_off + col]) : 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          if (chunk_of(ci) < n_chunks) {
             const uint32_t vb = vs + (uint32_t)ci * VEC_BYTES + (uint32_t)lane * 4;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb), "f"(bv) : "memory");
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 128), "f"(gv) : "memory");
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 256), "f"(cv) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb), "f"(pv_b[ci]) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 128), "f"(pv_g[ci]) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(vb + 256), "f"(has_nx ? pv_w[ci] * (1.f + pv_s[ci]) : 0.f) : "memory");
           }
         }
         __syncwarp();
+        if (tile + sched_n < num_tiles) vec_load(tile + sched_n);
         ptx::mbar_wait(&bars->tfull[as], aphase);
         ptx::tc_fence_after();
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
