@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VAVAE_ABI_VERSION 2
+#define VAVAE_ABI_VERSION 3
 
 /* precision modes */
 #define VAVAE_PREC_BF16 0 /* tcgen05 bf16 tensor-core path, fp32 accumulate / residual / statistics */
@@ -207,6 +207,13 @@ typedef struct vavae_epilogue_test {
   int32_t part_ld;          /* row pitch (floats) of in_part / nx_part */
 } vavae_epilogue_test_t;
 int vavae_test_gemm_epilogue(vavae_epilogue_test_t* t, void* stream);
+
+/* Host-only (no GPU needed): how the library would tile and run one layer GEMM of M token rows - the rules the parity
+ * of small and large batches rests on (tests/test_host_logic.py).  kind: VAVAE_EPI_*; T: tokens per sample; H, hd: QKV
+ * only; fused: the gated-residual launch also emits the next RMSNorm's operand and partial sums.
+ * out[6] = {column-tile width, width of the last column tile, 1 if the TMA epilogue runs, its epilogue warps (4 / 8),
+ *           its ring slots per warp, 1 if the launch writes coarse (128-column) partial-sum slots}. */
+int vavae_gemm_plan(int kind, int M, int N, int K, int T, int H, int hd, int fused, int32_t* out);
 
 /* 1: GEMMs use the CTA-pair kernel (cluster of 2, tcgen05 cta_group::2, M = 256 per pair) where the problem
  * allows it; 0: always the single-CTA kernel.  Process-wide; default set by the engine. */

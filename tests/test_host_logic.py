@@ -190,3 +190,57 @@ def test_bench_arms_describe_the_same_workload(tmp_path):
     assert line["impl"] == "reference" and line["config"]["workload"] == bench.workload_desc(a, 1)
     assert line["cpu_baseline"]["cores"] == (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["metric"] == bench.METRIC
+
+
+# ---- tile selection of the layer GEMMs (vavae_gemm_plan: host-only view of launch_gemm_tc's decisions) ----------------
+def _ctas(M, N, bn, bn_last):
+    cols = (N - bn_last) // bn + 1 if bn_last != bn else -(-N // bn)
+    return -(-M // 128) * cols
+
+
+def test_large_batch_layer_gemms_use_wide_tiles_and_the_tma_epilogue_where_it_measured_faster():
+    from va_vae_b200 import engine as E
+    M, T, D, S = 65536, 256, 1152, 3072                        # XL/1, 256 model rows
+    qkv = E.gemm_plan(E.EPI_QKV, M, 3 * D, D, T, H=16, hd=72)
+    assert (qkv["bn"], qkv["bn_last"]) == (256, 128)           # 3456 = 13 x 256 + 128
+    w12 = E.gemm_plan(E.EPI_SWIGLU, M, 2 * S, D, T)
+    assert (w12["bn"], w12["bn_last"]) == (256, 256)
+    proj = E.gemm_plan(E.EPI_GATED_RESIDUAL, M, D, D, T)
+    assert (proj["bn"], proj["bn_last"]) == (256, 128) and proj["tma"] and proj["warps"] == 8 and proj["coarse"]
+    w3 = E.gemm_plan(E.EPI_GATED_RESIDUAL, M, D, S, T)
+    assert w3["tma"] and w3["warps"] == 4 and w3["coarse"]     # long K: four epilogue warps keep the fifth operand stage
+    b1_w3 = E.gemm_plan(E.EPI_GATED_RESIDUAL, 131072, 768, 2048, T)
+    assert not b1_w3["tma"] and b1_w3["coarse"] and b1_w3["bn"] == 256   # measured slower on both TMA variants
+    # partial tile pairs (M % 256 != 0): the TMA epilogue needs guard-free geometry
+    assert not E.gemm_plan(E.EPI_GATED_RESIDUAL, 65536 + 128, D, D, T)["tma"]
+
+
+def test_small_batch_layer_gemms_use_narrow_tiles_within_one_wave():
+    from va_vae_b200 import engine as E
+    T, D, S = 256, 1152, 3072
+    for batch in (1, 2, 4, 8):
+        M = batch * T
+        for kind, N, K, kw in ((E.EPI_QKV, 3 * D, D, dict(H=16, hd=72)), (E.EPI_SWIGLU, 2 * S, D, {}),
+                               (E.EPI_GATED_RESIDUAL, D, D, {}), (E.EPI_GATED_RESIDUAL, D, S, {})):
+            p = E.gemm_plan(kind, M, N, K, T, **kw)
+            wide = _ctas(M, N, 256, 128 if N % 256 else 256)
+            assert p["bn"] % 32 == 0 and p["bn_last"] % 32 == 0
+            if p["bn"] != 256:                                  # narrowed: divides N, fits one wave, more CTAs than before
+                assert N % p["bn"] == 0 and p["bn_last"] == p["bn"]
+                assert wide < _ctas(M, N, p["bn"], p["bn"]) <= 148
+            if kind == E.EPI_GATED_RESIDUAL:                    # producers keep whole 128-column groups -> coarse slots
+                assert p["bn"] % 128 == 0 and p["coarse"]
+    assert E.gemm_plan(E.EPI_QKV, 256, 3 * D, D, T, H=16, hd=72)["bn"] == 64        # 108 CTAs
+    assert E.gemm_plan(E.EPI_SWIGLU, 256, 2 * S, D, T)["bn"] == 96                  # 128 CTAs
+    assert E.gemm_plan(E.EPI_GATED_RESIDUAL, 256, D, S, T)["bn"] == 128             # 18 CTAs, coarse slots
+
+
+def test_partial_sum_layout_follows_the_tile_width_not_the_batch():
+    """Coarse slots exactly when every tile holds whole 128-column groups; an odd hidden size gets fine slots at any M."""
+    from va_vae_b200 import engine as E
+    for M in (256, 4096, 65536):
+        for N in (384, 768, 1024, 1152):
+            p = E.gemm_plan(E.EPI_GATED_RESIDUAL, M, N, N, 256)
+            assert p["coarse"] == (p["bn"] % 128 == 0 and p["bn_last"] % 128 == 0) and p["coarse"]
+        p = E.gemm_plan(E.EPI_GATED_RESIDUAL, M, 96, 384, 32)
+        assert not p["coarse"] and p["bn"] == 96

@@ -1434,6 +1434,28 @@ int vavae_sde_update(const vavae_sde_update_t* u, void* stream) {
   }
 }
 
+// Host-only: how launch_gemm_tc would tile and run one layer GEMM (tests of the tile-selection rules; no GPU needed).
+int vavae_gemm_plan(int kind, int M, int N, int K, int T, int H, int hd, int fused, int32_t* out) {
+  try {
+    VV_CHECK(out && M > 0 && N > 0 && K > 0 && kind >= VAVAE_EPI_QKV && kind <= VAVAE_EPI_GATED_RESIDUAL, "gemm_plan: bad arguments");
+    const int epi = kind == VAVAE_EPI_QKV ? TC_EPI_QKV : (kind == VAVAE_EPI_SWIGLU ? TC_EPI_SWIGLU : TC_EPI_GATED_RESIDUAL);
+    bf16* fake = reinterpret_cast<bf16*>(uintptr_t(4096));   // aligned, never dereferenced
+    TcGemmArgs a = tc_args(fake, K, fake, K, M, N, K, epi, nullptr);
+    a.T = T; a.H = H; a.hd = hd;
+    if (epi == TC_EPI_GATED_RESIDUAL) {
+      a.out = fake; a.ldo = N; a.mod = reinterpret_cast<const float*>(fake);
+      if (fused) { a.nx_w = reinterpret_cast<const float*>(fake); a.nx_A = fake; }
+    }
+    int o[6];
+    gemm_tc_plan_query(a, o);
+    for (int i = 0; i < 6; ++i) out[i] = o[i];
+    return 0;
+  } catch (const std::exception& ex) {
+    g_err = ex.what();
+    return 1;
+  }
+}
+
 int vavae_set_gemm_two_cta(int on) {
   vv::set_gemm_two_cta(on);
   return 0;

@@ -1763,6 +1763,17 @@ static GatedPlan gated_plan(const TcGemmArgs& a, int BN) {
   return p;
 }
 int gemm_tc_part_coarse(const TcGemmArgs& a) { return gated_plan(a, gemm_tc_pick_bn(a)).coarse; }
+// host-only view of the decisions above, for tests of the tile-selection rules (no CUDA call)
+void gemm_tc_plan_query(const TcGemmArgs& a, int out[6]) {
+  const int BN = gemm_tc_pick_bn(a);
+  out[0] = BN;
+  out[1] = gemm_tc_last_bn(a, BN);
+  out[2] = out[3] = out[4] = out[5] = 0;
+  if (a.epi == TC_EPI_GATED_RESIDUAL) {
+    const GatedPlan p = gated_plan(a, BN);
+    out[2] = p.tma; out[3] = p.tma ? p.warps : 8; out[4] = p.tma ? p.slots : 0; out[5] = p.coarse;
+  }
+}
 int gemm_tc_part_ld(int n_cols, int coarse) { return coarse ? 16 : n_cols / 4; }
 
 void launch_gemm_tc(const TcGemmArgs& a, cudaStream_t s) {

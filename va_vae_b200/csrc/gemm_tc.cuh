@@ -106,6 +106,8 @@ int gemm_tc_part_coarse(const TcGemmArgs& a);
 // number of slots (coarse) / chunks (fine) a consumer sums, and the row pitch (floats) either layout needs
 inline int gemm_tc_part_slots(int n_cols, int coarse) { return coarse ? (n_cols + 127) / 128 : (n_cols + 31) / 32; }
 int gemm_tc_part_ld(int n_cols, int coarse);
+// {tile width, last tile width, TMA epilogue?, epilogue warps, ring slots, coarse slots?} of a launch (host only)
+void gemm_tc_plan_query(const TcGemmArgs& a, int out[6]);
 int gemm_tc_pick_bn(const TcGemmArgs& a);
 // 1: use the CTA-pair (cta_group::2) kernel where the problem allows it; 0: always the 1-CTA kernel
 void set_gemm_two_cta(int on);

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("VAVAE_B200_LIB") or os.path.join(_HERE, "libvavae_b20
 
 PREC_BF16, PREC_FP32 = 0, 1
 ODE_EULER, ODE_HEUN = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 SAMPLE_SKIP_DISCARDED = 1
 EPI_QKV, EPI_SWIGLU, EPI_GATED_RESIDUAL = 0, 1, 2
 
@@ -29,7 +29,7 @@ EXPORTS = [
     "vavae_profile_begin", "vavae_profile_end", "vavae_set_gemm_two_cta", "vavae_sample_dopri5",
     "vavae_device_status", "vavae_forward_rows", "vavae_test_gemm_epilogue", "vavae_sde_update",
     "vavae_decoder_create", "vavae_decoder_destroy", "vavae_decoder_load_weight", "vavae_decoder_finalize",
-    "vavae_decoder_decode", "vavae_decoder_launch_count", "vavae_decoder_device_bytes",
+    "vavae_decoder_decode", "vavae_decoder_launch_count", "vavae_decoder_device_bytes", "vavae_gemm_plan",
 ]
 
 
@@ -409,6 +409,16 @@ def test_gemm_epilogue(**fields) -> int:
         _check(lib.vavae_test_gemm_epilogue(ctypes.byref(t), ctypes.c_void_p(_stream(dev))))
     test_gemm_epilogue.fine_out = int(t.fine_out)   # kind of partial-sum slots a producer launch wrote (1 = 32-column)
     return int(t.nparts_out)
+
+
+def gemm_plan(kind: int, M: int, N: int, K: int, T: int, H: int = 0, hd: int = 0, fused: bool = True) -> dict:
+    """Host-only (vavae_gemm_plan): column-tile widths, epilogue variant and partial-sum layout the library picks for one
+    layer GEMM of M token rows.  No GPU needed."""
+    lib = load_library()
+    out = (ctypes.c_int32 * 6)()
+    _check(lib.vavae_gemm_plan(int(kind), int(M), int(N), int(K), int(T), int(H), int(hd), int(bool(fused)), out))
+    bn, bn_last, tma, warps, slots, coarse = (int(v) for v in out)
+    return dict(bn=bn, bn_last=bn_last, tma=bool(tma), warps=warps, slots=slots, coarse=bool(coarse))
 
 
 def sde_update(mode: int, x: torch.Tensor, out: torch.Tensor, v=None, w=None, k1=None, xh=None, out2=None, **scalars):
