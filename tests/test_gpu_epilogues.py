@@ -238,3 +238,34 @@ def test_fused_norm_consumer_fine_and_coarse_slots_agree_bitwise():
     U = (A.float() @ W12.float().t()) * rstd[:, None] + sp.repeat_interleave(T, 0)
     want = torch.nn.functional.silu(U[:, 0::2]) * U[:, 1::2]
     assert rel_l2(outs[0], want) < 3e-3
+
+
+def test_gated_residual_tma_epilogue_single_cta_matches_cta_pairs():
+    """The TMA epilogue also runs under the single-CTA kernel (developer knob set_gemm_two_cta(0)): same bits as CTA pairs."""
+    from va_vae_b200 import engine as E
+    dev = _dev()
+    T, M, N, K = 256, 768, 1152, 1152
+    A, W, bias = _operands(M, N, K, seed=17)
+    X0 = _rand(M, N, seed=1)
+    mod_ld, gate_off, scale_off = 3 * N + 8, 8, 8 + 2 * N
+    mod = _rand(M // T, mod_ld, seed=2, scale=0.5)
+    nx_w = 1 + 0.1 * _rand(N, seed=3)
+    res = []
+    try:
+        for two in (1, 0):
+            E.set_gemm_two_cta(two)
+            X = X0.clone().to(dev)
+            nxA = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+            part = torch.zeros(M, 16, device=dev)
+            n = E.test_gemm_epilogue(kind=E.EPI_GATED_RESIDUAL, M=M, N=N, K=K, T=T, A=A.to(dev), W=W.to(dev),
+                                     bias=bias.to(dev), X=X, mod=mod.to(dev), mod_ld=mod_ld, gate_off=gate_off,
+                                     nx_w=nx_w.to(dev), nx_scale_off=scale_off, nx_A=nxA, nx_part=part, part_ld=16)
+            torch.cuda.synchronize()
+            res.append((X, nxA, part[:, :n]))
+    finally:
+        E.set_gemm_two_cta(2)
+    gate = mod[:, gate_off: gate_off + N].repeat_interleave(T, 0)
+    want = X0 + gate * (A.float() @ W.float().t() + bias)
+    assert rel_l2(res[0][0], want) < 1e-5
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
