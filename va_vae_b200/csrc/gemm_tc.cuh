@@ -87,8 +87,9 @@ struct TcGemmArgs {
   // (M % 128 == 0, N % tile width == 0): launch_gemm_tc checks it.
   float* gn_part;
   int gn_hw, gn_cpg_shift;
-  // developer timing experiments on the gated-residual epilogue (VAVAE_GEMM_EXPERIMENT; results are WRONG when set):
-  // bit 0: no residual loads, bit 1: no next-operand stores, bit 2: no residual stores.  0 in production.
+  // developer timing experiments on the register-prefetch gated-residual epilogue (VAVAE_GEMM_EXPERIMENT; any value also
+  // disables the TMA epilogue).  Results are WRONG with bits 0-2: bit 0: no residual loads, bit 1: no next-operand
+  // stores, bit 2: no residual stores; bit 3: residual loads with L1::no_allocate (results unchanged).  0 in production.
   int experiment;
   // Row-tile order: 0 = ascending, 1 = descending.  The engine alternates it from one kernel of the layer stack to the
   // next so that a consumer starts on the rows its producer wrote LAST - the part of a larger-than-L2 tensor that is
