@@ -169,8 +169,8 @@ int vavae_test_attention_bf16(const void* q, const void* k, const void* vt, void
  * floats apart): COARSE, one float per 128-column group, summed in ascending order (in_nparts of them); or FINE
  * (in_fine = 1), eight floats per 32-column chunk (sums of squares of 4 columns each; in_nparts chunks), which the
  * consumer folds into exactly the coarse values first.  A producer (GATED_RESIDUAL with nx_w) reports which layout it
- * wrote in fine_out (wide tiles: coarse; narrow tiles of small-M launches: fine) and how many slots / chunks in
- * nparts_out. */
+ * wrote in fine_out (tiles of whole 128-column groups: coarse; tiles that split a group: fine) and how many slots /
+ * chunks in nparts_out. */
 #define VAVAE_EPI_QKV 0
 #define VAVAE_EPI_SWIGLU 1
 #define VAVAE_EPI_GATED_RESIDUAL 2

@@ -58,9 +58,10 @@ struct TcGemmArgs {
   // columns 32c + 4j .. 32c + 4j + 3, a COARSE slot (one float per 128-column group g) is
   //   fold8_j( ((s(4g, j) + s(4g+1, j)) + s(4g+2, j)) + s(4g+3, j) )
   // and the FINE slots of chunk c are the eight floats s(c, 0..7) (row pitch N / 4).  Which of the two a launch writes
-  // is gemm_tc_part_coarse(args): coarse needs one warp to own whole groups, i.e. 128 / 256-wide tiles; the narrow
-  // tiles of small-M launches write fine slots.  Both are pure functions of the row's values and a consumer folds
-  // fine slots into exactly the coarse values, so the tile shape - which depends on M - never changes a result.
+  // is gemm_tc_part_coarse(args): coarse needs one warp to own whole groups, i.e. 128 / 256-wide tiles (what every
+  // registry model gets at any M); tiles that split a group - hidden sizes that are not a multiple of 128 - write fine
+  // slots.  Both are pure functions of the row's values and a consumer folds fine slots into exactly the coarse
+  // values, so the tile shape - which depends on M - never changes a result.
   const float* nx_w;
   int nx_scale_off;
   bf16* nx_A;
