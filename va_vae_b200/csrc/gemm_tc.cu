@@ -1737,9 +1737,9 @@ static void launch_epi(const TcGemmArgs& a, int BN, int cw, cudaStream_t s) {
 struct GatedPlan { bool tma; int warps, slots, coarse; };
 static GatedPlan gated_plan(const TcGemmArgs& a, int BN) {
   GatedPlan p = {false, 8, 2, 0};
-  // VAVAE_GEMM_TMA_EPI (developer knob, same-box A/B): 0 = never, 1 = every eligible launch,
-  // 2 (default) = where it measured faster: attn.proj (K <= N: epilogue-bound), the long-K mlp.w3 of the XL model
-  // (main-loop-bound: four epilogue warps keep all five operand stages), and every small-M launch on narrow tiles
+  // VAVAE_GEMM_TMA_EPI (developer knob, same-box A/B): 0 = never; 1, 2 (default) = every eligible launch - eight epilogue
+  // warps for attn.proj (K <= N: epilogue-bound), four for mlp.w3 (K > N: main-loop-bound, the four idle warps' shared
+  // memory keeps all five operand stages): XL/1 w3 1230 -> 1320, B/1 w3 1240 -> 1280 TFLOP/s isolated; 3 = XL-only rule
   static int tma_epi = -1;
   if (tma_epi < 0) { const char* e = std::getenv("VAVAE_GEMM_TMA_EPI"); tma_epi = e ? std::atoi(e) : 2; }
   static int exp_mode = -1;
@@ -1750,13 +1750,17 @@ static GatedPlan gated_plan(const TcGemmArgs& a, int BN) {
                         (a.N % BN == 0 || a.N % BN == BNl) && a.ldo % 8 == 0 && a.N <= a.ldo &&
                         (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
                         (!a.nx_w || (reinterpret_cast<uintptr_t>(a.nx_A) & 15) == 0) && a.mod != nullptr;
-  const bool wanted = tma_epi == 1 || a.K <= a.N || a.K >= 3072 || BN <= 128;
+  // 3: the rule before the tile-ahead vectors (K <= N or K >= 3072 only), kept for A/B
+  const bool wanted = tma_epi == 1 || tma_epi == 2 || BN <= 128 || (tma_epi == 3 && (a.K <= a.N || a.K >= 3072));
   p.tma = tma_epi != 0 && exp_mode == 0 && eligible && wanted;
   if (p.tma) {
     static int xt_env = -1;   // VAVAE_GEMM_XT_SLOTS: developer knob, ring depth per epilogue warp
     if (xt_env < 0) { const char* e = std::getenv("VAVAE_GEMM_XT_SLOTS"); xt_env = e ? std::atoi(e) : 0; }
     p.slots = (xt_env >= 2 && xt_env <= XT_MAX_SLOTS) ? xt_env : 2;
     p.warps = (a.K <= a.N && BN > 128) ? 8 : 4;
+    static int xw_env = -1;   // VAVAE_GEMM_XT_WARPS: developer knob (4 / 8), wide tiles only
+    if (xw_env < 0) { const char* e = std::getenv("VAVAE_GEMM_XT_WARPS"); xw_env = e ? std::atoi(e) : 0; }
+    if ((xw_env == 4 || xw_env == 8) && BN > 128) p.warps = xw_env;
   }
   // a CTA (and within it one warp) must own whole 128-column groups
   p.coarse = (BN % 128 == 0 && BNl % 128 == 0) ? 1 : 0;
